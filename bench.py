@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline metric on B200: Jacobi-PCG DOF*iter/s (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        this implementation (CUDA, sm_100a)
+  python bench.py --impl reference ...                       the reference's own CPU path, host cores
+
+Workload at N=1: BASELINE.json configs[1] -- synthetic structured-quad cantilever, 1000x500 quads,
+1 003 002 DOF, plane stress, assembled ON THE DEVICE, Jacobi-PCG from x0 = 0 to |g| <= 1e-8 |b|
+(SURVEY.md §8d input 2).  For N>1 the mesh grows with N (1000 x 500N quads, slabs of grid lines per
+rank: weak scaling, ~1M DOF per GPU).
+
+One "step" = one complete solve.  `value` = DOF * iterations / device time with everything resident in
+HBM; `e2e` = the same solve through the reference-facing entry point
+nb_sparse_solve_CG_precond_Jacobi (libnbots_b200.so) with a host-resident nb_sparse_t and host vectors,
+all copies inside the timed region.  `roofline` is the SpMV+dot kernel of the solver (the dominant
+kernel) timed live with CUDA events on the library's stream.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from nbots_b200 import meshgen  # noqa: E402
+
+METRIC = "pcg_dof_iter_per_s"
+UNIT = "DOF*iter/s"
+NX, NY_PER_GPU = 1000, 500
+E_MOD, POISSON, THICKNESS = 1.0, 0.3, 1.0
+REL_TOL = 1e-8
+
+
+def workload_mesh(n_gpus):
+    nx, ny = NX, NY_PER_GPU * n_gpus
+    return meshgen.structured_mesh(nx, ny, 2.0, 1.0 * n_gpus, kind=1)
+
+
+def workload_bcs():
+    # clamp side x=0 (segment 3), total traction (0,-1) on side x=L (segment 1)
+    return [("dirichlet", "sgm", 3, (1, 1), (0.0, 0.0)), ("neumann", "sgm", 1, (1, 1), (0.0, -1.0))]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side nb_sparse_t (struct nb_sparse_s, sparse_struct.h:6-11) for the e2e call: the per-row
+# pointers index one flat block, which is all the reference-facing entry point can observe.
+class NbSparse(C.Structure):
+    _fields_ = [("rows_values", C.POINTER(C.c_void_p)), ("rows_index", C.POINTER(C.c_void_p)),
+                ("rows_size", C.POINTER(C.c_uint32)), ("N", C.c_uint32)]
+
+
+def host_nb_sparse(rows_size, cols, vals):
+    rp = np.zeros(rows_size.size + 1, dtype=np.uint64)
+    np.cumsum(rows_size, out=rp[1:])
+    pv = (vals.ctypes.data + rp[:-1] * 8).astype(np.uint64)
+    pc = (cols.ctypes.data + rp[:-1] * 4).astype(np.uint64)
+    A = NbSparse(pv.ctypes.data_as(C.POINTER(C.c_void_p)), pc.ctypes.data_as(C.POINTER(C.c_void_p)),
+                 rows_size.ctypes.data_as(C.POINTER(C.c_uint32)), rows_size.size)
+    return A, (pv, pc, rp)
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        return rank, world, dist
+    return rank, world, None
+
+
+def run_ours(args):
+    from nbots_b200 import api, capi
+    rank, world, dist = dist_setup(args.gpus)
+    if world > 1:
+        from nbots_b200 import multigpu
+        return multigpu.bench(args, rank, world, dist)
+
+    L = capi.lib()
+    capi.check(L.nbgpu_init(int(os.environ.get("LOCAL_RANK", "0"))))
+    t_setup = time.perf_counter()
+    m = workload_mesh(1)
+    rs, cols = api.pattern_from_mesh(m)
+    K = api.Matrix.from_csr(rs, cols)
+    mesh = api.Mesh(m)
+    d_F = api.DeviceBuffer.zeros(K.N)
+    api.sync()
+    api.timer_start()
+    st, _ = mesh.assemble(K, d_F, E_MOD, POISSON, thickness=THICKNESS)
+    ms_assembly = api.timer_stop()
+    assert st == 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import flatten_bcs
+    neu_dof, neu_add, dir_dof, dir_val = flatten_bcs(m, workload_bcs())
+    api.vector_add_entries(d_F, neu_dof, neu_add)
+    K.apply_dirichlet(d_F, dir_dof, dir_val)
+    b = d_F.to_host()
+    tol = REL_TOL * float(np.linalg.norm(b))
+    N, nnz = K.N, K.nnz
+    d_x = api.DeviceBuffer.zeros(N)
+    t_setup = time.perf_counter() - t_setup
+
+    def solve_resident():
+        capi.check(L.nbgpu_memset(d_x.ptr, 0, N * 8))
+        api.timer_start()
+        st, it, res = K.pcg_jacobi(d_F, d_x, max_iter=N, tol=tol)
+        return api.timer_stop(), st, it, res
+
+    for _ in range(args.warmup):
+        solve_resident()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    launches0 = api.launch_count()
+    times, iters = [], 0
+    for _ in range(args.steps):
+        ms, st, it, res = solve_resident()
+        times.append(ms)
+        iters = it
+        assert st == 0, "solve did not converge"
+    launches = api.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_step = float(np.mean(times))
+    value = N * iters / (ms_step * 1e-3)
+    x_resident = d_x.to_host()
+
+    # ---- dominant kernel, live: CUDA events around each kernel of 256 iterations ------------------
+    capi.check(L.nbgpu_krylov_profile(1))
+    capi.check(L.nbgpu_memset(d_x.ptr, 0, N * 8))
+    K.pcg_jacobi(d_F, d_x, max_iter=256, tol=0.0)
+    capi.check(L.nbgpu_krylov_profile(0))
+    ms3 = np.zeros(3); n_prof = C.c_uint32(0)
+    capi.check(L.nbgpu_krylov_profile_get(ms3.ctypes.data_as(capi.f64p), C.byref(n_prof)))
+    per = ms3 / max(1, n_prof.value)
+    peak, peak_src = measured_peaks()
+    bytes_spmv = 12 * nnz + 20 * N + 4          # SURVEY.md §8d, K1 (CSR-equivalent algorithmic bytes)
+    bytes_update, bytes_dir = 64 * N, 24 * N     # K2, K3
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("krylov_spmv_kernel_dram_bytes_per_launch")
+    ach = bytes_spmv / (per[0] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "krylov_spmv_kernel (SpMV + p.w)", "achieved": round(ach, 1),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": traffic, "algorithmic_bytes_per_launch": bytes_spmv,
+                "ms_per_launch": round(float(per[0]), 5), "launches_timed": int(n_prof.value),
+                "other_kernels": {
+                    "krylov_update_kernel": {"ms": round(float(per[1]), 5),
+                                             "GB/s": round(bytes_update / (per[1] * 1e-3) / 1e9, 1)},
+                    "krylov_dir_kernel": {"ms": round(float(per[2]), 5),
+                                          "GB/s": round(bytes_dir / (per[2] * 1e-3) / 1e9, 1)}},
+                "iteration_bytes_model": 12 * nnz + 108 * N,
+                "iteration_GBps": round((12 * nnz + 108 * N) * iters / (ms_step * 1e-3) / 1e9, 1)}
+
+    # ---- e2e: the reference-facing call with host buffers --------------------------------------------
+    vals = K.values_csr()
+    A_host, keep = host_nb_sparse(rs, cols, vals)
+    shim = C.CDLL(capi.SHIM_PATH)
+    fn = shim.nb_sparse_solve_CG_precond_Jacobi
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(NbSparse), capi.f64p, capi.f64p, C.c_uint32, C.c_double, capi.u32p, capi.f64p,
+                   C.c_uint32]
+    x_host = np.zeros(N)
+    e2e_times, e2e_iters = [], 0
+    for k in range(2 + args.steps):
+        x_host[:] = 0.0
+        it = C.c_uint32(0); res = C.c_double(0)
+        api.sync()
+        t0 = time.perf_counter()
+        st = fn(C.byref(A_host), b.ctypes.data_as(capi.f64p), x_host.ctypes.data_as(capi.f64p), N, tol,
+                C.byref(it), C.byref(res), 1)
+        dt = time.perf_counter() - t0
+        assert st == 0, capi.lib().nbgpu_last_error()
+        if k >= 2:
+            e2e_times.append(dt)
+        e2e_iters = it.value
+    e2e_value = N * e2e_iters / float(np.mean(e2e_times))
+    assert np.array_equal(x_host, x_resident), "e2e and resident solves must be the same computation"
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz + 16 * N),
+           "d2h_bytes_per_step": int(8 * N), "ms_per_step": round(float(np.mean(e2e_times)) * 1e3, 2),
+           "entry_point": "nb_sparse_solve_CG_precond_Jacobi (libnbots_b200.so), host nb_sparse_t"}
+
+    cpu = cpu_baseline(m, b, tol, x_resident, vals, d_F_host=b) if not args.no_cpu_baseline else None
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Q1: structured-quad cantilever 1000x500, plane stress, Jacobi-PCG to 1e-8*|b| "
+                                   "(BASELINE.json configs[1])",
+                       "N_dof": N, "nnz": int(nnz), "iterations_per_step": int(iters), "rel_tol": REL_TOL,
+                       "l2": "working set 265 MB (matrix 216 MB + 6 vectors) exceeds the 126 MB L2; no flush",
+                       "assembly_ms_on_device": round(ms_assembly, 3), "setup_s": round(t_setup, 2)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_system(m):
+    """The workload's linear system built by the REFERENCE'S OWN CPU pipeline (oracle/_ref), or by the
+    pinned port when the compiled reference is not available.  -> (kind, solver object, b)"""
+    from oracle import port, ref
+    bcs = workload_bcs()
+    if ref.available():
+        rm = ref.RefMesh.from_arrays(m)
+        K = ref.RefSparse.from_mesh(rm)
+        st, F = ref.assemble(K, rm, 1, E_MOD, POISSON, thickness=THICKNESS)
+        bc = ref.RefBcond()
+        for r in bcs:
+            bc.push(*r)
+        ref.set_bconditions(rm, K, F, bc)
+        return "reference", K, F
+    rs, cols = port.pattern_from_mesh(m)
+    K = port.Csr(rs, cols)
+    st, F = port.assemble(K, m, E_MOD, POISSON, thickness=THICKNESS)
+    port.set_bconditions(m, K, F, bcs)
+    return "port", K, F
+
+
+def time_cpu_pcg(K, b, threads, budget_s):
+    """Bounded sample: a fixed number of PCG iterations from x0 = 0 sized for ~budget_s seconds."""
+    t0 = time.perf_counter()
+    K.pcg_jacobi(b, max_iter=10, tol=0.0, threads=threads)
+    per_iter = (time.perf_counter() - t0) / 10
+    n_it = int(min(2000, max(20, budget_s / per_iter)))
+    t0 = time.perf_counter()
+    st, x, it, res = K.pcg_jacobi(b, max_iter=n_it, tol=0.0, threads=threads)
+    dt = time.perf_counter() - t0
+    return it, dt
+
+
+def cpu_baseline(m, b_gpu, tol, x_gpu, vals_gpu, d_F_host):
+    cores = os.cpu_count() or 1
+    kind, K, F = reference_system(m)
+    vals_ref = K.export()[2] if kind == "reference" else K.vals
+    it, dt = time_cpu_pcg(K, F, cores, 12.0)
+    N = F.size
+    return {"value": N * it / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{it} Jacobi-PCG iterations of the same Q1 system from x0=0 "
+                      f"({dt:.1f} s, omp_parallel_threads={cores})",
+            "fullsize_parity": {"K_bit_exact": bool(np.array_equal(vals_ref, vals_gpu)),
+                                "F_bit_exact": bool(np.array_equal(F, b_gpu))}}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path, all host threads; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    m = workload_mesh(args.gpus)
+    kind, K, F = reference_system(m)
+    N = F.size
+    tot_it, tot_t = 0, 0.0
+    per_step_budget = max(2.0, 40.0 / max(1, args.steps + args.warmup))
+    for k in range(args.warmup + args.steps):
+        it, dt = time_cpu_pcg(K, F, cores, per_step_budget)
+        if k >= args.warmup:
+            tot_it += it
+            tot_t += dt
+    value = N * tot_it / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(tot_t / args.steps * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Q1 x {args.gpus}: structured-quad cantilever {NX}x{NY_PER_GPU * args.gpus}, "
+                                   "plane stress, Jacobi-PCG (BASELINE.json configs[1])", "N_dof": int(N)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{tot_it // args.steps} PCG iterations per step from x0=0, "
+                                       f"nb_sparse_solve_CG_precond_Jacobi with omp_parallel_threads={cores}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

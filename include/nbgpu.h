@@ -1,0 +1,328 @@
+/*
+ * nbgpu.h -- C ABI of the B200 (sm_100a) implementation of the NBOTS hot path:
+ * Jacobi-PCG / CG / SpMV over the Solver bot's nb_sparse_t and the PDE bot's
+ * 2-D linear-elastic FEM assembly that feeds it.
+ *
+ * This header is the drop-in boundary.  Everything is
+ * `extern "C"`, plain pointers and sizes; no CUDA or torch types appear in a
+ * signature.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference tree).  The reference-named wrappers
+ * (nb_sparse_solve_CG_precond_Jacobi, ... ) that a maintainer links in front
+ * of libnbots live in nbots_b200/csrc/shim/ and are described in
+ * INTEGRATION.md.
+ *
+ * Conventions kept from the reference (README_DEVELOPERS.md:52,82-90):
+ *   - int return codes, 0 = success;
+ *   - solver: 0 converged, 1 = max_iter reached (cg_precond_jacobi.c:86-89);
+ *   - assembly: 0 ok, 1 = distorted element (pipeline.c:53-72, utils.c:44-47);
+ *   - new failure classes use codes >= 10 (callers only test `0 != status`);
+ *   - caller owns every buffer it passes; `x` is in (initial guess) / out.
+ * Pointers named d_* are DEVICE pointers (from nbgpu_malloc); all others are
+ * host pointers.  There is no CPU fallback: without a usable CUDA device every
+ * compute call fails with NBGPU_ERR_CUDA.
+ */
+#ifndef NBGPU_H
+#define NBGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBGPU_OK                 0
+#define NBGPU_NOT_CONVERGED      1   /* solver: max_iter reached            */
+#define NBGPU_DISTORTED_ELEMENT  1   /* assembly: detJ < 0 somewhere        */
+#define NBGPU_ERR_CUDA          10   /* CUDA runtime / no device            */
+#define NBGPU_ERR_ARG           11   /* invalid argument                    */
+#define NBGPU_ERR_PATTERN       12   /* entry not in the sparsity pattern
+                                        (reference: printf + exit(1),
+                                        sparse.c:213-217)                   */
+#define NBGPU_ERR_NOMEM         13
+#define NBGPU_ERR_COMM          14   /* multi-GPU exchange failed           */
+
+typedef struct nbgpu_matrix_s nbgpu_matrix_t;   /* device-resident nb_sparse_t */
+typedef struct nbgpu_mesh_s nbgpu_mesh_t;       /* device-resident FEM mesh    */
+
+/* ------------------------------------------------------------ context -- */
+
+/* Bind this process to `device` (-1: LOCAL_RANK env, else 0) and create the
+ * work stream.  Idempotent; compute calls do it lazily with -1. */
+int nbgpu_init(int device);
+int nbgpu_finalize(void);
+int nbgpu_device_count(void);
+int nbgpu_sync(void);
+/* text of the last error raised on the calling thread ("" if none) */
+const char *nbgpu_last_error(void);
+/* the cudaStream_t every kernel of this library is launched on */
+void *nbgpu_stream(void);
+/* number of kernels this library has launched so far (for `gpu_launches`) */
+uint64_t nbgpu_launch_count(void);
+
+int nbgpu_malloc(void **d_ptr, size_t bytes);
+int nbgpu_free(void *d_ptr);
+int nbgpu_memset(void *d_ptr, int byte, size_t bytes);
+int nbgpu_copy_h2d(void *d_dst, const void *src, size_t bytes);
+int nbgpu_copy_d2h(void *dst, const void *d_src, size_t bytes);
+int nbgpu_copy_d2d(void *d_dst, const void *d_src, size_t bytes);
+/* pinned host memory (H2D/D2H at full PCIe rate) */
+int nbgpu_host_alloc(void **ptr, size_t bytes);
+int nbgpu_host_free(void *ptr);
+/* stream-ordered timing with CUDA events on the library's stream */
+int nbgpu_timer_start(void);
+int nbgpu_timer_stop(float *elapsed_ms);
+
+/* ------------------------------------------------------------- matrix -- */
+/* Replaces the storage of struct nb_sparse_s
+ * (sources/nb/solver_bot/sparse/sparse_struct.h:6-11): per-row heap blocks
+ * become one SELL-32 (sliced ELLPACK, slice = one warp of rows) block in HBM.
+ * The pattern (rows_size, ascending unique columns) is kept bit for bit. */
+
+/* from the jagged arrays of an nb_sparse_t (what nb_sparse_create returns,
+ * sparse.c:20-60); rows_values == NULL means all-zero values */
+int nbgpu_matrix_create_from_rows(uint32_t N, const uint32_t *rows_size,
+				  uint32_t *const *rows_index,
+				  double *const *rows_values,
+				  nbgpu_matrix_t **out);
+/* from flat CSR arrays (rows concatenated); vals == NULL means zeros */
+int nbgpu_matrix_create_from_csr(uint32_t N, const uint32_t *rows_size,
+				 const uint32_t *cols, const double *vals,
+				 nbgpu_matrix_t **out);
+int nbgpu_matrix_destroy(nbgpu_matrix_t *A);
+/* N, nnz, slices, stored (padded) entries */
+int nbgpu_matrix_info(const nbgpu_matrix_t *A, uint32_t *N, uint64_t *nnz,
+		      uint32_t *n_slices, uint64_t *stored_entries);
+int nbgpu_matrix_set_values_rows(nbgpu_matrix_t *A, double *const *rows_values);
+int nbgpu_matrix_set_values_csr(nbgpu_matrix_t *A, const double *vals);
+int nbgpu_matrix_get_values_rows(const nbgpu_matrix_t *A, double *const *rows_values);
+int nbgpu_matrix_get_values_csr(const nbgpu_matrix_t *A, double *vals);
+/* pattern back out, CSR order (for the bit-exactness checks) */
+int nbgpu_matrix_get_pattern_csr(const nbgpu_matrix_t *A, uint32_t *rows_size,
+				 uint32_t *cols);
+/* nb_sparse_reset (sparse.c:127-132) */
+int nbgpu_matrix_reset(nbgpu_matrix_t *A);
+
+/* ---------------------------------------------------------------- SpMV -- */
+/* nb_sparse_multiply_vector (sparse.c:405-414): out = A in.  Each row is
+ * summed in ascending column order with separately rounded products and sums,
+ * i.e. the same floating-point result as the reference loop. */
+int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out);
+int nbgpu_spmv_host(const nbgpu_matrix_t *A, const double *in, double *out);
+
+/* -------------------------------------------------------------- Krylov -- */
+/* nb_sparse_solve_CG_precond_Jacobi (solvers/cg_precond_jacobi.c:13-90,
+ * header solvers/cg_precond_jacobi.h:8-15) and
+ * nb_sparse_solve_conjugate_gradient (solvers/conjugate_gradient.c:13-77).
+ * Same stopping rule: absolute, `while (g.g > tol^2 && k < max_iter)` with the
+ * residual of the iterate BEFORE the last update; tol_reached = sqrt of that
+ * same quantity.  niter / tol_reached may be NULL. */
+int nbgpu_pcg_jacobi(const nbgpu_matrix_t *A, const double *d_b, double *d_x,
+		     uint32_t max_iter, double tolerance,
+		     uint32_t *niter_performed, double *tolerance_reached);
+int nbgpu_cg(const nbgpu_matrix_t *A, const double *d_b, double *d_x,
+	     uint32_t max_iter, double tolerance,
+	     uint32_t *niter_performed, double *tolerance_reached);
+/* host-buffer forms: upload b and x, solve, download x */
+int nbgpu_pcg_jacobi_host(const nbgpu_matrix_t *A, const double *b, double *x,
+			  uint32_t max_iter, double tolerance,
+			  uint32_t *niter_performed, double *tolerance_reached);
+int nbgpu_cg_host(const nbgpu_matrix_t *A, const double *b, double *x,
+		  uint32_t max_iter, double tolerance,
+		  uint32_t *niter_performed, double *tolerance_reached);
+
+/* Per-kernel timing of the solvers: when enabled, CUDA events bracket the three
+ * kernels of each of the first 256 iterations of the next solves, on the
+ * library's stream.  _get returns the summed durations [SpMV+dot, update,
+ * direction] in ms and the number of iterations they cover (last solve). */
+int nbgpu_krylov_profile(int enable);
+int nbgpu_krylov_profile_get(double ms_total[3], uint32_t *n_iters);
+
+/* ------------------------------------------------------- FEM assembly -- */
+
+/* node graph + pattern on the host, bit-exact with
+ * nb_mesh2D_load_graph(NB_NODES_LINKED_BY_ELEMS) (mesh2D/load_graph.c:230-328)
+ * followed by nb_sparse_create(graph, NULL, vars_per_node) (sparse.c:20-60).
+ * edg may be NULL (the edges of a conforming mesh are element sides).  Call
+ * with cols == NULL to size the output (rows_size is filled, nnz returned). */
+int nbgpu_pattern_from_mesh(uint32_t N_nod, uint32_t N_elems,
+			    uint32_t nodes_per_elem, const uint32_t *adj,
+			    uint32_t N_edg, const uint32_t *edg,
+			    uint32_t vars_per_node, uint32_t *rows_size,
+			    uint32_t *cols, uint64_t *nnz);
+
+/* mesh arrays as in struct nb_mshquad_s / nb_msh3trg_s (mshquad_struct.h:6-26):
+ * nod[2*N_nod] x,y interleaved; adj[nodes_per_elem*N_elems] CCW connectivity;
+ * nodes_per_elem is 3 or 4 for the whole mesh */
+int nbgpu_mesh_create(uint32_t N_nod, const double *nod, uint32_t N_elems,
+		      uint32_t nodes_per_elem, const uint32_t *adj,
+		      nbgpu_mesh_t **out);
+int nbgpu_mesh_destroy(nbgpu_mesh_t *mesh);
+
+/* element tables as struct nb_fem_elem_s holds them (element_struct.h:8-16),
+ * indexed [node * N_gp + gp] (element.c:144-160) */
+typedef struct {
+	uint32_t N_nodes;      /* 3 or 4 */
+	uint32_t N_gp;         /* 1 or 4 */
+	double gp_weight[4];
+	double Ni[16];
+	double dNi_dpsi[16];
+	double dNi_deta[16];
+} nbgpu_elem_tables_t;
+
+/* the reference's own tables (element.c:54-121), 12-digit quad literals */
+int nbgpu_elem_tables_default(uint32_t nodes_per_elem, nbgpu_elem_tables_t *t);
+/* nb_pde_get_constitutive_matrix (common_solid_mechanics/formulas.c:32-63),
+ * including its switch fall-through: plane-stress D for every analysis id */
+int nbgpu_constitutive_matrix(double E, double poisson, int analysis2D,
+			      double D[4]);
+
+#define NBGPU_ASSEMBLY_GATHER  0  /* row-parallel gather, bit-exact order   */
+#define NBGPU_ASSEMBLY_ATOMIC  1  /* element-parallel, atomicAdd(double)    */
+#define NBGPU_ASSEMBLY_COLOR   2  /* element-parallel, colour-scheduled     */
+
+typedef struct {
+	double D[4];           /* enabled elements (a12)                       */
+	double density;
+	double D_void[4];      /* disabled elements: 1e-6 x4 (pipeline.c:93)   */
+	double density_void;   /* 1e-6 (pipeline.c:94)                         */
+	double thickness;      /* params2D->thickness                          */
+	int32_t self_weight;
+	double gravity[2];
+	int32_t mode;          /* NBGPU_ASSEMBLY_*                             */
+} nbgpu_assembly_params_t;
+
+/* pipeline_assemble_system (solid_mechanics/pipeline.c:42-73 and the helpers
+ * down to :264; utils.c:9-60): resets K, zeroes F, integrates every element
+ * (B'DB detJ t w per Gauss point) into K and the self-weight into F.
+ * enabled: host array, one byte per element, NULL = all enabled.
+ * elem_scale: optional host array of per-element stiffness factors applied to
+ * D of enabled elements (SIMP-style loops); NULL = 1.
+ * Returns 0, or 1 if any element has detJ < 0 (first_bad gets the lowest such
+ * element id when not NULL). */
+int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh,
+				const nbgpu_elem_tables_t *tables,
+				const nbgpu_assembly_params_t *params,
+				const uint8_t *enabled,
+				const double *elem_scale, double *d_F,
+				uint32_t *first_bad);
+
+/* F[dof[k]] += add[k], k in order (the Neumann part of nb_fem_set_bconditions,
+ * solid_mechanics/set_bconditions.c:63-188, flattened by the caller) */
+int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof,
+			     const double *add);
+
+/* nb_sparse_set_Dirichlet_condition (sparse.c:416-430) for a list of
+ * constrained dofs applied in list order (set_bconditions.c:190-262) */
+int nbgpu_apply_dirichlet(nbgpu_matrix_t *K, double *d_F, uint32_t n,
+			  const uint32_t *dof, const double *value);
+
+/* pipeline_compute_strain (pipeline.c:266-319): strain[3*N_gp*N_elems] */
+int nbgpu_compute_strain(const nbgpu_mesh_t *mesh,
+			 const nbgpu_elem_tables_t *tables,
+			 const double *d_disp, double *d_strain);
+/* nb_fem_compute_stress_from_strain (static_elasticity2D.c:99-127) */
+int nbgpu_stress_from_strain(uint32_t N_elems, uint32_t N_gp,
+			     const double D[4], const double D_void[4],
+			     const uint8_t *enabled, const double *d_strain,
+			     double *d_stress);
+
+/* ------------------------------------------- boundary-condition lists -- */
+
+/* value callback of a function-valued condition, as nb_bcond_push_function
+ * takes it (headers/nb/pde_bot/boundary_conditions/bcond.h) */
+typedef void (*nbgpu_bc_fn)(const double *x, double t, double *out);
+
+/* one nb_bcond_push / nb_bcond_push_function call (bcond.c:153-165) */
+typedef struct {
+	int32_t kind;          /* 0 Dirichlet, 1 Neumann (nb_bcond_id)           */
+	int32_t where;         /* 0 input vertex, 1 input segment (nb_bcond_where) */
+	uint32_t id;           /* input vertex / segment id                       */
+	int32_t mask[2];       /* dof mask                                        */
+	double val[2];         /* constant value (ignored when fval != NULL)      */
+	nbgpu_bc_fn fval;      /* NULL = constant                                 */
+} nbgpu_bcond_t;
+
+/* Host side of nb_fem_set_bconditions (solid_mechanics/set_bconditions.c:52-262):
+ * turns the condition queues into two ORDERED dof lists -- Neumann adds
+ * (segments first, then vertices) and Dirichlet (dof, value) pairs (segments
+ * first, then vertices) -- with exactly the reference's arithmetic for the
+ * nodal shares.  Call with the output arrays NULL to get the counts. */
+int nbgpu_bcond_flatten(const double *nod, const uint32_t *vtx,
+			uint32_t N_sgm, const uint32_t *sgm_sizes,
+			const uint32_t *sgm_nodes, uint32_t N_bc,
+			const nbgpu_bcond_t *bc, double factor,
+			uint32_t *n_neumann, uint32_t *neumann_dof,
+			double *neumann_add, uint32_t *n_dirichlet,
+			uint32_t *dirichlet_dof, double *dirichlet_val);
+
+/* ------------------------------------------------------- FEM driver -- */
+
+/* flat view of a struct nb_mshquad_s / nb_msh3trg_s mesh */
+typedef struct {
+	uint32_t N_nod;
+	const double *nod;          /* [2 N_nod]                                */
+	uint32_t N_elems;
+	uint32_t nodes_per_elem;    /* 3 or 4                                   */
+	const uint32_t *adj;        /* [nodes_per_elem N_elems]                 */
+	uint32_t N_edg;
+	const uint32_t *edg;        /* [2 N_edg] or NULL                        */
+	uint32_t N_vtx;
+	const uint32_t *vtx;        /* mesh node of every input vertex          */
+	uint32_t N_sgm;
+	const uint32_t *sgm_sizes;  /* nodes per input segment                  */
+	const uint32_t *sgm_nodes;  /* concatenated node ids along the segments */
+} nbgpu_mesh_desc_t;
+
+typedef struct {
+	uint32_t N;                 /* dofs                                     */
+	uint64_t nnz;
+	uint32_t solver_iters;
+	int32_t solver_status;      /* 0 converged, 1 max_iter                  */
+	double solver_residual;     /* tolerance_reached                        */
+	double ms_pattern, ms_upload, ms_assembly, ms_bcond, ms_solve, ms_post;
+} nbgpu_fem_report_t;
+
+/* nb_fem_compute_2D_Solid_Mechanics
+ * (solid_mechanics/static_elasticity2D.c:31-97, header
+ * headers/nb/pde_bot/finite_element/solid_mechanics/static_elasticity2D.h:13-24):
+ * pattern -> assembly -> boundary conditions -> Jacobi-PCG (x0 = 0, abs tol
+ * 1e-8, max_iter = N; status 1 accepted like :92) -> strain.  K, F and the
+ * iterates never leave the device.  Returns 0, or 1 when assembly met a
+ * distorted element (then displacement/strain are untouched), or >= 10.
+ * tables == NULL uses nbgpu_elem_tables_default; solver_tol <= 0 means the
+ * reference's 1e-8; report may be NULL. */
+/* Same pipeline with the boundary conditions already flattened into ordered
+ * dof lists (what nbgpu_bcond_flatten produces) and the constitutive matrix
+ * given directly; this is the form the reference-named shim uses after
+ * walking the reference's own nb_bcond_t and calling its own
+ * nb_pde_get_constitutive_matrix. */
+int nbgpu_fem_static_elasticity2d_lists(const nbgpu_mesh_desc_t *mesh,
+					const nbgpu_elem_tables_t *tables,
+					const double D[4], double density,
+					uint32_t n_neumann,
+					const uint32_t *neumann_dof,
+					const double *neumann_add,
+					uint32_t n_dirichlet,
+					const uint32_t *dirichlet_dof,
+					const double *dirichlet_val,
+					int self_weight, const double gravity[2],
+					int analysis2D, double thickness,
+					const uint8_t *enabled, int assembly_mode,
+					double solver_tol, double *displacement,
+					double *strain, nbgpu_fem_report_t *report);
+
+int nbgpu_fem_static_elasticity2d(const nbgpu_mesh_desc_t *mesh,
+				  const nbgpu_elem_tables_t *tables,
+				  double E, double poisson, double density,
+				  uint32_t N_bc, const nbgpu_bcond_t *bc,
+				  int self_weight, const double gravity[2],
+				  int analysis2D, double thickness,
+				  const uint8_t *enabled, int assembly_mode,
+				  double solver_tol, double *displacement,
+				  double *strain, nbgpu_fem_report_t *report);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBGPU_H */

@@ -1,0 +1,874 @@
+// assembly.cu -- 2-D linear-elastic FEM stiffness assembly straight into the
+// SELL-32 matrix, boundary conditions, strain/stress recovery.
+//
+// Reference: pipeline_assemble_system and helpers
+//   (sources/nb/pde_bot/finite_element/solid_mechanics/pipeline.c:42-264),
+//   nb_fem_get_jacobian / nb_fem_get_derivatives (finite_element/utils.c:9-60),
+//   element tables (finite_element/element.c:54-121),
+//   nb_sparse_set_Dirichlet_condition (solver_bot/sparse/sparse.c:416-430),
+//   pipeline_compute_strain (pipeline.c:266-319),
+//   nb_fem_compute_stress_from_strain (static_elasticity2D.c:99-127).
+//
+// This file is compiled with -fmad=false: every product and sum is rounded
+// separately, in the reference's expression order, so element matrices come
+// out bit-identical to the reference's (x86-64 without FMA).
+//
+// Three assembly schedules write the same values:
+//   GATHER  one thread per matrix ROW.  The thread walks the elements around
+//           its node in ascending element id and adds its own row of each
+//           element matrix into its own SELL row: no atomics, coalesced
+//           stores, and every K entry receives its contributions in the same
+//           order as the reference's serial element loop -> bit-exact K and F.
+//   ATOMIC  one thread per ELEMENT, full Ke in registers, scattered with
+//           atomicAdd(double) (RED.ADD.F64); order is nondeterministic, values
+//           agree to rounding.
+//   COLOR   one thread per element, one launch per colour of a greedy
+//           element colouring (no two elements of a colour share a node), plain
+//           read-modify-write; deterministic, colour order instead of id order.
+// The reference has no colouring code; the greedy colouring here
+// is this library's own.
+#include <algorithm>
+#include <cstring>
+
+#include "matrix.cuh"
+
+using namespace nbgpu;
+
+struct nbgpu_mesh_s {
+	uint32_t N_nod = 0, N_elems = 0, npe = 0;
+	double *d_nod = nullptr;          // [2 N_nod]
+	uint32_t *d_adj = nullptr;        // [npe N_elems]
+	uint32_t *d_n2e_ptr = nullptr;    // [N_nod + 1] elements around each node ...
+	uint32_t *d_n2e = nullptr;        // [npe N_elems] ... ascending element id
+	uint8_t *d_enabled = nullptr;     // [N_elems] scratch for the enabled mask
+	double *d_scale = nullptr;        // [N_elems] scratch for per-element factors
+	std::vector<uint32_t> h_adj;      // host copy (colouring is built lazily)
+	uint32_t n_colors = 0;
+	std::vector<uint32_t> color_ptr;  // [n_colors + 1]
+	uint32_t *d_color_elems = nullptr;
+};
+
+namespace {
+
+struct ElemTables {
+	double w[4], Ni[16], dpsi[16], deta[16];
+};
+
+struct AsmParams {
+	double D[4], D_void[4];
+	double density, density_void, thickness;
+	double gx, gy;
+	int self_weight;
+};
+
+__constant__ ElemTables c_tab;
+
+// Jacobian and Cartesian gradients at Gauss point gp (utils.c:9-41, :49-60).
+template <int NPE, int NGP>
+__device__ __forceinline__ double jacobian_gradients(const double (&xs)[NPE], const double (&ys)[NPE],
+						      int gp, double (&dNdx)[NPE], double (&dNdy)[NPE])
+{
+	double x_psi = 0.0, y_psi = 0.0, x_eta = 0.0, y_eta = 0.0;
+#pragma unroll
+	for (int i = 0; i < NPE; i++) {
+		const double dp = c_tab.dpsi[i * NGP + gp], de = c_tab.deta[i * NGP + gp];
+		x_psi += dp * xs[i];
+		x_eta += de * xs[i];
+		y_psi += dp * ys[i];
+		y_eta += de * ys[i];
+	}
+	const double detJ = x_psi * y_eta - y_psi * x_eta;
+	const double j0 = y_eta / detJ, j1 = -y_psi / detJ, j2 = -x_eta / detJ, j3 = x_psi / detJ;
+#pragma unroll
+	for (int i = 0; i < NPE; i++) {
+		const double dp = c_tab.dpsi[i * NGP + gp], de = c_tab.deta[i * NGP + gp];
+		dNdx[i] = j0 * dp + j1 * de;
+		dNdy[i] = j2 * dp + j3 * de;
+	}
+	return detJ;
+}
+
+__device__ __forceinline__ void element_material(const AsmParams &P, const uint8_t *enabled,
+						 const double *scale, uint32_t e, double (&D)[4],
+						 double &rho)
+{
+	if (!enabled || enabled[e]) {
+		// pipeline.c:95-98; the optional factor scales the enabled material (SIMP-style)
+		const double s = scale ? scale[e] : 1.0;
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			D[k] = scale ? P.D[k] * s : P.D[k];
+		rho = P.density;
+	} else {
+		// pipeline.c:93-94: "void" material, including the off-diagonal 1e-6
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			D[k] = P.D_void[k];
+		rho = P.density_void;
+	}
+}
+
+// position of column `c` in SELL row `row` (entries j < width), or SIZE_MAX
+__device__ __forceinline__ size_t find_in_row(const uint32_t *__restrict__ col, uint32_t off,
+					      uint32_t width, uint32_t lane, uint32_t c)
+{
+	const uint32_t *p = col + (size_t)off * kSliceRows + lane;
+	for (uint32_t j = 0; j < width; j++) {
+		const uint32_t cj = p[(size_t)j * kSliceRows];
+		if (cj == c)
+			return ((size_t)off + j) * kSliceRows + lane;
+		if (cj > c)   // ascending columns; padding is 0xFFFFFFFF
+			break;
+	}
+	return (size_t)-1;
+}
+
+// ---- GATHER: one thread per matrix row -------------------------------------
+template <int NPE, int NGP>
+__global__ void __launch_bounds__(kBlock)
+assemble_gather_kernel(uint32_t N_nod, const double *__restrict__ nod, const uint32_t *__restrict__ adj,
+		       const uint32_t *__restrict__ n2e_ptr, const uint32_t *__restrict__ n2e,
+		       const uint8_t *__restrict__ enabled, const double *__restrict__ scale, AsmParams P,
+		       const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ col,
+		       double *__restrict__ val, double *__restrict__ F, unsigned int *first_bad,
+		       int *pattern_miss)
+{
+	const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= 2 * N_nod)
+		return;
+	const uint32_t node = row >> 1, a = row & 1, lane = row & 31;
+	const uint32_t off = slice_off[row >> 5], width = slice_off[(row >> 5) + 1] - off;
+	double f_acc = 0.0;
+	for (uint32_t t = n2e_ptr[node]; t < n2e_ptr[node + 1]; t++) {
+		const uint32_t e = n2e[t];
+		uint32_t v[NPE];
+		double xs[NPE], ys[NPE];
+		int li = 0;
+#pragma unroll
+		for (int i = 0; i < NPE; i++) {
+			v[i] = adj[(size_t)e * NPE + i];
+			xs[i] = nod[2 * (size_t)v[i]];
+			ys[i] = nod[2 * (size_t)v[i] + 1];
+		}
+#pragma unroll
+		for (int i = NPE - 1; i >= 0; i--)
+			if (v[i] == node)
+				li = i;   // first local index of this node
+		double D[4], rho;
+		element_material(P, enabled, scale, e, D, rho);
+		const double fa = P.self_weight ? (a ? P.gy : P.gx) * rho : 0.0;
+		double kv[2 * NPE];   // row (2 li + a) of Ke
+#pragma unroll
+		for (int c = 0; c < 2 * NPE; c++)
+			kv[c] = 0.0;
+		double fe = 0.0;
+		bool bad = false;
+#pragma unroll
+		for (int gp = 0; gp < NGP; gp++) {
+			double dx[NPE], dy[NPE];
+			const double detJ = jacobian_gradients<NPE, NGP>(xs, ys, gp, dx, dy);
+			if (detJ < 0)
+				bad = true;   // utils.c:44-47
+			const double wp = c_tab.w[gp];
+			double dxi = dx[0], dyi = dy[0], Ni = c_tab.Ni[gp];
+#pragma unroll
+			for (int i = 1; i < NPE; i++)
+				if (li == i) {
+					dxi = dx[i];
+					dyi = dy[i];
+					Ni = c_tab.Ni[i * NGP + gp];
+				}
+#pragma unroll
+			for (int j = 0; j < NPE; j++) {
+				// pipeline.c:196-214, row a of the 2x2 block (li, j)
+				if (a == 0) {
+					kv[2 * j] += (dxi * dx[j] * D[0] + dyi * dy[j] * D[3]) * detJ *
+						     P.thickness * wp;
+					kv[2 * j + 1] += (dxi * dy[j] * D[1] + dyi * dx[j] * D[3]) * detJ *
+							 P.thickness * wp;
+				} else {
+					kv[2 * j] += (dyi * dx[j] * D[1] + dxi * dy[j] * D[3]) * detJ *
+						     P.thickness * wp;
+					kv[2 * j + 1] += (dyi * dy[j] * D[2] + dxi * dx[j] * D[3]) * detJ *
+							 P.thickness * wp;
+				}
+			}
+			const double integral = Ni * detJ * P.thickness * wp;   // pipeline.c:225-228
+			fe += integral * fa;
+		}
+		if (bad) {
+			atomicMin(first_bad, e);
+			continue;
+		}
+#pragma unroll
+		for (int j = 0; j < NPE; j++) {
+#pragma unroll
+			for (int b = 0; b < 2; b++) {
+				const size_t pos = find_in_row(col, off, width, lane, 2 * v[j] + b);
+				if (pos == (size_t)-1) {
+					*pattern_miss = 1;   // sparse.c:213-217
+					continue;
+				}
+				val[pos] += kv[2 * j + b];
+			}
+		}
+		f_acc += fe;
+	}
+	F[row] = f_acc;
+}
+
+// ---- ATOMIC / COLOR: one thread per element --------------------------------
+template <int NPE, int NGP, bool ATOMIC>
+__global__ void __launch_bounds__(128)
+assemble_element_kernel(uint32_t n_work, const uint32_t *__restrict__ work /* null = identity */,
+			const double *__restrict__ nod, const uint32_t *__restrict__ adj,
+			const uint8_t *__restrict__ enabled, const double *__restrict__ scale, AsmParams P,
+			const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ col,
+			double *__restrict__ val, double *__restrict__ F, unsigned int *first_bad,
+			int *pattern_miss)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_work)
+		return;
+	const uint32_t e = work ? work[t] : t;
+	uint32_t v[NPE];
+	double xs[NPE], ys[NPE];
+#pragma unroll
+	for (int i = 0; i < NPE; i++) {
+		v[i] = adj[(size_t)e * NPE + i];
+		xs[i] = nod[2 * (size_t)v[i]];
+		ys[i] = nod[2 * (size_t)v[i] + 1];
+	}
+	double D[4], rho;
+	element_material(P, enabled, scale, e, D, rho);
+	const double fx = P.self_weight ? P.gx * rho : 0.0, fy = P.self_weight ? P.gy * rho : 0.0;
+	double Ke[4 * NPE * NPE], Fe[2 * NPE];
+#pragma unroll
+	for (int k = 0; k < 4 * NPE * NPE; k++)
+		Ke[k] = 0.0;
+#pragma unroll
+	for (int k = 0; k < 2 * NPE; k++)
+		Fe[k] = 0.0;
+	bool bad = false;
+#pragma unroll
+	for (int gp = 0; gp < NGP; gp++) {
+		double dx[NPE], dy[NPE];
+		const double detJ = jacobian_gradients<NPE, NGP>(xs, ys, gp, dx, dy);
+		if (detJ < 0)
+			bad = true;
+		const double wp = c_tab.w[gp];
+#pragma unroll
+		for (int i = 0; i < NPE; i++) {
+#pragma unroll
+			for (int j = 0; j < NPE; j++) {
+				Ke[(2 * i) * (2 * NPE) + 2 * j] +=
+					(dx[i] * dx[j] * D[0] + dy[i] * dy[j] * D[3]) * detJ * P.thickness * wp;
+				Ke[(2 * i) * (2 * NPE) + 2 * j + 1] +=
+					(dx[i] * dy[j] * D[1] + dy[i] * dx[j] * D[3]) * detJ * P.thickness * wp;
+				Ke[(2 * i + 1) * (2 * NPE) + 2 * j] +=
+					(dy[i] * dx[j] * D[1] + dx[i] * dy[j] * D[3]) * detJ * P.thickness * wp;
+				Ke[(2 * i + 1) * (2 * NPE) + 2 * j + 1] +=
+					(dy[i] * dy[j] * D[2] + dx[i] * dx[j] * D[3]) * detJ * P.thickness * wp;
+			}
+			const double integral = c_tab.Ni[i * NGP + gp] * detJ * P.thickness * wp;
+			Fe[2 * i] += integral * fx;
+			Fe[2 * i + 1] += integral * fy;
+		}
+	}
+	if (bad) {
+		atomicMin(first_bad, e);
+		return;
+	}
+#pragma unroll
+	for (int i = 0; i < NPE; i++) {
+#pragma unroll
+		for (int a = 0; a < 2; a++) {
+			const uint32_t row = 2 * v[i] + a;
+			const uint32_t off = slice_off[row >> 5], width = slice_off[(row >> 5) + 1] - off;
+#pragma unroll
+			for (int j = 0; j < NPE; j++) {
+#pragma unroll
+				for (int b = 0; b < 2; b++) {
+					const size_t pos = find_in_row(col, off, width, row & 31, 2 * v[j] + b);
+					if (pos == (size_t)-1) {
+						*pattern_miss = 1;
+						continue;
+					}
+					const double k = Ke[(2 * i + a) * (2 * NPE) + 2 * j + b];
+					if (ATOMIC)
+						atomicAdd(val + pos, k);
+					else
+						val[pos] += k;
+				}
+			}
+			if (P.self_weight) {
+				if (ATOMIC)
+					atomicAdd(F + row, Fe[2 * i + a]);
+				else
+					F[row] += Fe[2 * i + a];
+			}
+		}
+	}
+}
+
+// ---- boundary conditions ---------------------------------------------------
+
+// F[dof[k]] += add[k] in list order.  The lists are boundary-sized; one thread
+// keeps the order of the reference's sequential adds (set_bconditions.c:156-170).
+__global__ void vector_add_entries_kernel(double *F, uint32_t n, const uint32_t *__restrict__ dof,
+					  const double *__restrict__ add)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		for (uint32_t k = 0; k < n; k++)
+			F[dof[k]] += add[k];
+}
+
+// nb_sparse_set_Dirichlet_condition applied for a whole ordered list at once.
+// order[i] = 1 + position of dof i's FIRST occurrence in the list (0 = free),
+// v_first / v_last = its first / last prescribed value.  Sequential semantics
+// reproduced per row (sparse.c:416-430):
+//   constrained row i : identity row, F[i] = last value written for i;
+//   free row i        : every entry (i,c) with c constrained is zeroed and
+//                       F[i] -= A_ic * v_first[c], subtracted in the order the
+//                       constraints were applied (ascending order[c]).
+__global__ void __launch_bounds__(kBlock)
+dirichlet_kernel(uint32_t N, const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ col,
+		 double *__restrict__ val, double *__restrict__ F, const uint32_t *__restrict__ order,
+		 const double *__restrict__ v_first, const double *__restrict__ v_last)
+{
+	const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= N)
+		return;
+	const uint32_t lane = row & 31;
+	const uint32_t off = slice_off[row >> 5], width = slice_off[(row >> 5) + 1] - off;
+	const uint32_t *cp = col + (size_t)off * kSliceRows + lane;
+	double *vp = val + (size_t)off * kSliceRows + lane;
+	const uint32_t my = order[row];
+	if (my) {
+		for (uint32_t j = 0; j < width; j++) {
+			const uint32_t c = cp[(size_t)j * kSliceRows];
+			if (c == kPadCol)
+				break;
+			vp[(size_t)j * kSliceRows] = (c == row) ? 1.0 : 0.0;
+		}
+		F[row] = v_last[my - 1];
+		return;
+	}
+	uint32_t last = 0;
+	double f = F[row];
+	bool touched = false;
+	for (;;) {
+		uint32_t best = 0xFFFFFFFFu, best_j = 0;
+		for (uint32_t j = 0; j < width; j++) {
+			const uint32_t c = cp[(size_t)j * kSliceRows];
+			if (c == kPadCol)
+				break;
+			const uint32_t o = order[c];
+			if (o > last && o < best) {
+				best = o;
+				best_j = j;
+			}
+		}
+		if (best == 0xFFFFFFFFu)
+			break;
+		const double a = vp[(size_t)best_j * kSliceRows];
+		vp[(size_t)best_j * kSliceRows] = 0.0;
+		f -= a * v_first[best - 1];
+		touched = true;
+		last = best;
+	}
+	if (touched)
+		F[row] = f;
+}
+
+// ---- strain / stress -------------------------------------------------------
+template <int NPE, int NGP>
+__global__ void __launch_bounds__(kBlock)
+strain_kernel(uint32_t N_elems, const double *__restrict__ nod, const uint32_t *__restrict__ adj,
+	      const double *__restrict__ disp, double *__restrict__ strain)
+{
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= N_elems)
+		return;
+	uint32_t v[NPE];
+	double xs[NPE], ys[NPE], ux[NPE], uy[NPE];
+#pragma unroll
+	for (int i = 0; i < NPE; i++) {
+		v[i] = adj[(size_t)e * NPE + i];
+		xs[i] = nod[2 * (size_t)v[i]];
+		ys[i] = nod[2 * (size_t)v[i] + 1];
+		ux[i] = disp[2 * (size_t)v[i]];
+		uy[i] = disp[2 * (size_t)v[i] + 1];
+	}
+	bool stop = false;
+#pragma unroll
+	for (int gp = 0; gp < NGP; gp++) {
+		double dx[NPE], dy[NPE];
+		const double detJ = jacobian_gradients<NPE, NGP>(xs, ys, gp, dx, dy);
+		if (detJ < 0)
+			stop = true;   // pipeline.c:302-303: the element stops at its first bad point
+		double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+		if (!stop) {
+#pragma unroll
+			for (int i = 0; i < NPE; i++) {
+				s0 += dx[i] * ux[i];
+				s1 += dy[i] * uy[i];
+				s2 += (dy[i] * ux[i] + dx[i] * uy[i]);
+			}
+		}
+		double *s = strain + 3 * ((size_t)e * NGP + gp);
+		s[0] = s0;
+		s[1] = s1;
+		s[2] = s2;
+	}
+}
+
+__global__ void __launch_bounds__(kBlock)
+stress_kernel(uint32_t N_elems, uint32_t NGP, const uint8_t *__restrict__ enabled, double D0, double D1,
+	      double D2, double D3, double V0, double V1, double V2, double V3,
+	      const double *__restrict__ strain, double *__restrict__ stress)
+{
+	const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= (size_t)N_elems * NGP)
+		return;
+	const uint32_t e = (uint32_t)(id / NGP);
+	const bool en = !enabled || enabled[e];
+	const double d0 = en ? D0 : V0, d1 = en ? D1 : V1, d2 = en ? D2 : V2, d3 = en ? D3 : V3;
+	const double *s = strain + 3 * id;
+	double *t = stress + 3 * id;
+	const double s0 = s[0], s1 = s[1], s2 = s[2];
+	t[0] = s0 * d0 + s1 * d1;
+	t[1] = s0 * d1 + s1 * d2;
+	t[2] = s2 * d3;
+}
+
+// ---- host helpers ------------------------------------------------------------
+
+int upload_tables(const nbgpu_elem_tables_t *t, uint32_t npe)
+{
+	NB_ARG(t != nullptr && t->N_nodes == npe);
+	NB_ARG((npe == 3 && t->N_gp == 1) || (npe == 4 && t->N_gp == 4));
+	ElemTables h;
+	memcpy(h.w, t->gp_weight, sizeof(h.w));
+	memcpy(h.Ni, t->Ni, sizeof(h.Ni));
+	memcpy(h.dpsi, t->dNi_dpsi, sizeof(h.dpsi));
+	memcpy(h.deta, t->dNi_deta, sizeof(h.deta));
+	NB_CUDA(cudaMemcpyToSymbolAsync(c_tab, &h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx().stream));
+	NB_CUDA(cudaStreamSynchronize(ctx().stream));   // `h` is a stack object
+	return NBGPU_OK;
+}
+
+// greedy colouring in element order: colour(e) = lowest colour not yet used by
+// an element sharing a node with e
+int build_coloring(nbgpu_mesh_t *m)
+{
+	if (m->n_colors)
+		return NBGPU_OK;
+	std::vector<uint64_t> used(m->N_nod, 0);
+	std::vector<uint8_t> color(m->N_elems);
+	uint32_t n_colors = 0;
+	for (uint32_t e = 0; e < m->N_elems; e++) {
+		uint64_t mask = 0;
+		for (uint32_t i = 0; i < m->npe; i++)
+			mask |= used[m->h_adj[(size_t)e * m->npe + i]];
+		if (~mask == 0) {
+			set_error("element colouring needs more than 64 colours");
+			return NBGPU_ERR_ARG;
+		}
+		const uint32_t cidx = (uint32_t)__builtin_ctzll(~mask);
+		color[e] = (uint8_t)cidx;
+		n_colors = std::max(n_colors, cidx + 1);
+		for (uint32_t i = 0; i < m->npe; i++)
+			used[m->h_adj[(size_t)e * m->npe + i]] |= 1ull << cidx;
+	}
+	m->color_ptr.assign(n_colors + 1, 0);
+	for (uint32_t e = 0; e < m->N_elems; e++)
+		m->color_ptr[color[e] + 1]++;
+	for (uint32_t c = 0; c < n_colors; c++)
+		m->color_ptr[c + 1] += m->color_ptr[c];
+	std::vector<uint32_t> next(m->color_ptr.begin(), m->color_ptr.end() - 1), elems(m->N_elems);
+	for (uint32_t e = 0; e < m->N_elems; e++)
+		elems[next[color[e]]++] = e;
+	NB_CUDA(cudaMalloc(&m->d_color_elems, std::max<size_t>(1, m->N_elems) * sizeof(uint32_t)));
+	NB_CUDA(cudaMemcpy(m->d_color_elems, elems.data(), (size_t)m->N_elems * sizeof(uint32_t),
+			   cudaMemcpyHostToDevice));
+	m->n_colors = n_colors;
+	return NBGPU_OK;
+}
+
+template <int NPE, int NGP>
+int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int mode, const uint8_t *d_en,
+		    const double *d_scale, double *d_F, unsigned int *d_bad, int *d_miss)
+{
+	Context &c = ctx();
+	if (mode == NBGPU_ASSEMBLY_GATHER) {
+		const uint32_t rows = 2 * m->N_nod;
+		assemble_gather_kernel<NPE, NGP><<<(rows + kBlock - 1) / kBlock, kBlock, 0, c.stream>>>(
+			m->N_nod, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, P, K->d_slice_off,
+			K->d_col, K->d_val, d_F, d_bad, d_miss);
+		NB_LAUNCHED();
+	} else if (mode == NBGPU_ASSEMBLY_ATOMIC) {
+		NB_CUDA(cudaMemsetAsync(d_F, 0, 2 * (size_t)m->N_nod * sizeof(double), c.stream));
+		assemble_element_kernel<NPE, NGP, true><<<(m->N_elems + 127) / 128, 128, 0, c.stream>>>(
+			m->N_elems, nullptr, m->d_nod, m->d_adj, d_en, d_scale, P, K->d_slice_off, K->d_col,
+			K->d_val, d_F, d_bad, d_miss);
+		NB_LAUNCHED();
+	} else {
+		NB_TRY(build_coloring(m));
+		NB_CUDA(cudaMemsetAsync(d_F, 0, 2 * (size_t)m->N_nod * sizeof(double), c.stream));
+		for (uint32_t col = 0; col < m->n_colors; col++) {
+			const uint32_t n = m->color_ptr[col + 1] - m->color_ptr[col];
+			if (!n)
+				continue;
+			assemble_element_kernel<NPE, NGP, false><<<(n + 127) / 128, 128, 0, c.stream>>>(
+				n, m->d_color_elems + m->color_ptr[col], m->d_nod, m->d_adj, d_en, d_scale, P,
+				K->d_slice_off, K->d_col, K->d_val, d_F, d_bad, d_miss);
+			NB_LAUNCHED();
+		}
+	}
+	return NBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nbgpu_elem_tables_default(uint32_t nodes_per_elem, nbgpu_elem_tables_t *t)
+{
+	NB_ARG(t != nullptr && (nodes_per_elem == 3 || nodes_per_elem == 4));
+	memset(t, 0, sizeof(*t));
+	t->N_nodes = nodes_per_elem;
+	if (nodes_per_elem == 3) {
+		// element.c:54-73
+		t->N_gp = 1;
+		t->gp_weight[0] = 0.5;
+		for (int i = 0; i < 3; i++)
+			t->Ni[i] = 0.33333333333333333333333333333;
+		t->dNi_dpsi[0] = -1.0; t->dNi_dpsi[1] = 1.0; t->dNi_dpsi[2] = 0.0;
+		t->dNi_deta[0] = -1.0; t->dNi_deta[1] = 0.0; t->dNi_deta[2] = 1.0;
+		return NBGPU_OK;
+	}
+	// element.c:75-121.  Bilinear shape functions at the 2x2 Gauss points
+	// (+-1/sqrt3), corners and points both ordered (-,-),(+,-),(+,+),(-,+).
+	// The reference tabulates them with 12 significant digits; those rounded
+	// literals (not the exact values) are what parity requires.
+	t->N_gp = 4;
+	const double n_near = 0.622008467928, n_side = 0.166666666667, n_far = 0.044658198739;
+	const double d_near = 0.394337567297, d_far = 0.105662432703;
+	const int sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
+	for (int g = 0; g < 4; g++)
+		t->gp_weight[g] = 1.0;
+	for (int c = 0; c < 4; c++)
+		for (int g = 0; g < 4; g++) {
+			const bool same_x = sx[c] == sx[g], same_y = sy[c] == sy[g];
+			t->Ni[c * 4 + g] = (same_x && same_y) ? n_near : (same_x || same_y) ? n_side : n_far;
+			t->dNi_dpsi[c * 4 + g] = sx[c] * (same_y ? d_near : d_far);
+			t->dNi_deta[c * 4 + g] = sy[c] * (same_x ? d_near : d_far);
+		}
+	return NBGPU_OK;
+}
+
+int nbgpu_constitutive_matrix(double E, double poisson, int analysis2D, double D[4])
+{
+	NB_ARG(D != nullptr);
+	// formulas.c:38-45: the switch has no `break`, so NB_PLANE_STRESS,
+	// NB_PLANE_STRAIN and NB_SOLID_OF_REVOLUTION all end in set_plane_stress
+	// (formulas.c:48-54).  Kept on purpose: parity with the reference.
+	(void)analysis2D;
+	D[0] = E / (1.0 - poisson * poisson);
+	D[1] = poisson * D[0];
+	D[2] = D[0];
+	D[3] = E / (2.0 * (1.0 + poisson));
+	return NBGPU_OK;
+}
+
+int nbgpu_mesh_create(uint32_t N_nod, const double *nod, uint32_t N_elems, uint32_t nodes_per_elem,
+		      const uint32_t *adj, nbgpu_mesh_t **out)
+{
+	NB_INIT();
+	NB_ARG(out != nullptr && nod != nullptr && adj != nullptr);
+	NB_ARG(nodes_per_elem == 3 || nodes_per_elem == 4);
+	const uint32_t npe = nodes_per_elem;
+	for (size_t k = 0; k < (size_t)npe * N_elems; k++)
+		NB_ARG(adj[k] < N_nod);
+	nbgpu_mesh_t *m = new nbgpu_mesh_t();
+	m->N_nod = N_nod;
+	m->N_elems = N_elems;
+	m->npe = npe;
+	m->h_adj.assign(adj, adj + (size_t)npe * N_elems);
+	// elements around each node, ascending element id (counting sort)
+	std::vector<uint32_t> ptr((size_t)N_nod + 1, 0), n2e((size_t)npe * N_elems);
+	for (size_t k = 0; k < (size_t)npe * N_elems; k++)
+		ptr[adj[k] + 1]++;
+	for (uint32_t i = 0; i < N_nod; i++)
+		ptr[i + 1] += ptr[i];
+	{
+		std::vector<uint32_t> next(ptr.begin(), ptr.end() - 1);
+		for (uint32_t e = 0; e < N_elems; e++)
+			for (uint32_t i = 0; i < npe; i++) {
+				const uint32_t v = adj[(size_t)e * npe + i];
+				// a node listed twice in one element is visited once
+				if (next[v] > ptr[v] && n2e[next[v] - 1] == e)
+					continue;
+				n2e[next[v]++] = e;
+			}
+		// compact (only needed if some element repeated a node)
+		bool compact = false;
+		for (uint32_t i = 0; i < N_nod && !compact; i++)
+			compact = next[i] != ptr[i + 1];
+		if (compact) {
+			std::vector<uint32_t> ptr2((size_t)N_nod + 1, 0), n2e2;
+			for (uint32_t i = 0; i < N_nod; i++) {
+				n2e2.insert(n2e2.end(), n2e.begin() + ptr[i], n2e.begin() + next[i]);
+				ptr2[i + 1] = (uint32_t)n2e2.size();
+			}
+			n2e2.resize((size_t)npe * N_elems);
+			ptr.swap(ptr2);
+			n2e.swap(n2e2);
+		}
+	}
+	cudaError_t e = cudaMalloc(&m->d_nod, std::max<size_t>(1, 2 * (size_t)N_nod) * sizeof(double));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&m->d_adj, std::max<size_t>(1, (size_t)npe * N_elems) * sizeof(uint32_t));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&m->d_n2e_ptr, ptr.size() * sizeof(uint32_t));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&m->d_n2e, std::max<size_t>(1, n2e.size()) * sizeof(uint32_t));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&m->d_enabled, std::max<size_t>(1, N_elems));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&m->d_scale, std::max<size_t>(1, N_elems) * sizeof(double));
+	if (e == cudaSuccess)
+		e = cudaMemcpy(m->d_nod, nod, 2 * (size_t)N_nod * sizeof(double), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(m->d_adj, adj, (size_t)npe * N_elems * sizeof(uint32_t), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(m->d_n2e_ptr, ptr.data(), ptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(m->d_n2e, n2e.data(), n2e.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) {
+		set_error("mesh upload: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		nbgpu_mesh_destroy(m);
+		return NBGPU_ERR_CUDA;
+	}
+	*out = m;
+	return NBGPU_OK;
+}
+
+int nbgpu_mesh_destroy(nbgpu_mesh_t *m)
+{
+	if (!m)
+		return NBGPU_OK;
+	if (ctx().ready) {
+		cudaSetDevice(ctx().device);
+		cudaStreamSynchronize(ctx().stream);
+		cudaFree(m->d_nod);
+		cudaFree(m->d_adj);
+		cudaFree(m->d_n2e_ptr);
+		cudaFree(m->d_n2e);
+		cudaFree(m->d_enabled);
+		cudaFree(m->d_scale);
+		cudaFree(m->d_color_elems);
+	}
+	delete m;
+	return NBGPU_OK;
+}
+
+int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
+				const nbgpu_elem_tables_t *tables, const nbgpu_assembly_params_t *params,
+				const uint8_t *enabled, const double *elem_scale, double *d_F,
+				uint32_t *first_bad)
+{
+	NB_INIT();
+	nbgpu_mesh_t *m = const_cast<nbgpu_mesh_t *>(mesh_c);
+	NB_ARG(K != nullptr && m != nullptr && params != nullptr && d_F != nullptr);
+	NB_ARG(K->N == 2 * m->N_nod);
+	NB_ARG(params->mode >= NBGPU_ASSEMBLY_GATHER && params->mode <= NBGPU_ASSEMBLY_COLOR);
+	Context &c = ctx();
+	NB_TRY(upload_tables(tables, m->npe));
+	AsmParams P;
+	memcpy(P.D, params->D, sizeof(P.D));
+	memcpy(P.D_void, params->D_void, sizeof(P.D_void));
+	P.density = params->density;
+	P.density_void = params->density_void;
+	P.thickness = params->thickness;
+	P.self_weight = params->self_weight != 0;
+	P.gx = P.self_weight ? params->gravity[0] : 0.0;
+	P.gy = P.self_weight ? params->gravity[1] : 0.0;
+	const uint8_t *d_en = nullptr;
+	const double *d_scale = nullptr;
+	if (enabled) {
+		NB_CUDA(cudaMemcpyAsync(m->d_enabled, enabled, m->N_elems, cudaMemcpyHostToDevice, c.stream));
+		d_en = m->d_enabled;
+	}
+	if (elem_scale) {
+		NB_CUDA(cudaMemcpyAsync(m->d_scale, elem_scale, (size_t)m->N_elems * sizeof(double),
+					cudaMemcpyHostToDevice, c.stream));
+		d_scale = m->d_scale;
+	}
+	// flags: [0] lowest distorted element id, [1] pattern miss
+	unsigned int *d_flags = nullptr;
+	NB_CUDA(cudaMalloc(&d_flags, 2 * sizeof(unsigned int)));
+	const unsigned int init_flags[2] = {0xFFFFFFFFu, 0u};
+	NB_CUDA(cudaMemcpyAsync(d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, c.stream));
+	// nb_sparse_reset (pipeline.c:54) -- F is zeroed/overwritten by the kernels (pipeline.c:57)
+	NB_CUDA(cudaMemsetAsync(K->d_val, 0, K->stored * sizeof(double), c.stream));
+	int st;
+	if (m->npe == 3)
+		st = launch_assembly<3, 1>(K, m, P, params->mode, d_en, d_scale, d_F, d_flags, (int *)(d_flags + 1));
+	else
+		st = launch_assembly<4, 4>(K, m, P, params->mode, d_en, d_scale, d_F, d_flags, (int *)(d_flags + 1));
+	unsigned int h_flags[2] = {0xFFFFFFFFu, 0u};
+	cudaError_t e = cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c.stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(c.stream);
+	cudaFree(d_flags);
+	if (st != NBGPU_OK)
+		return st;
+	if (e != cudaSuccess) {
+		set_error("assembly: %s", cudaGetErrorString(e));
+		return NBGPU_ERR_CUDA;
+	}
+	if (h_flags[1]) {
+		set_error("assembly: an element entry is not in the sparsity pattern "
+			  "(the reference exits here, sparse.c:213-217)");
+		return NBGPU_ERR_PATTERN;
+	}
+	if (first_bad)
+		*first_bad = h_flags[0];
+	return h_flags[0] != 0xFFFFFFFFu ? NBGPU_DISTORTED_ELEMENT : NBGPU_OK;
+}
+
+int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof, const double *add)
+{
+	NB_INIT();
+	if (n == 0)
+		return NBGPU_OK;
+	NB_ARG(d_F != nullptr && dof != nullptr && add != nullptr);
+	Context &c = ctx();
+	void *buf = nullptr;
+	NB_CUDA(cudaMalloc(&buf, (size_t)n * (sizeof(uint32_t) + sizeof(double))));
+	double *d_add = (double *)buf;
+	uint32_t *d_dof = (uint32_t *)(d_add + n);
+	cudaError_t e = cudaMemcpyAsync(d_add, add, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d_dof, dof, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream);
+	if (e == cudaSuccess) {
+		vector_add_entries_kernel<<<1, 32, 0, c.stream>>>(d_F, n, d_dof, d_add);
+		ctx().launches++;
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(c.stream);
+	cudaFree(buf);
+	if (e != cudaSuccess) {
+		set_error("vector_add_entries: %s", cudaGetErrorString(e));
+		return NBGPU_ERR_CUDA;
+	}
+	return NBGPU_OK;
+}
+
+int nbgpu_apply_dirichlet(nbgpu_matrix_t *K, double *d_F, uint32_t n, const uint32_t *dof,
+			  const double *value)
+{
+	NB_INIT();
+	if (n == 0)
+		return NBGPU_OK;
+	NB_ARG(K != nullptr && d_F != nullptr && dof != nullptr && value != nullptr);
+	Context &c = ctx();
+	const uint32_t N = K->N;
+	// flatten the ordered list: first occurrence decides the elimination order
+	// and the value moved to the right-hand side, the last occurrence decides
+	// F[dof] (see dirichlet_kernel)
+	std::vector<uint32_t> order(N, 0);
+	std::vector<double> v_first, v_last;
+	v_first.reserve(n);
+	v_last.reserve(n);
+	for (uint32_t k = 0; k < n; k++) {
+		NB_ARG(dof[k] < N);
+		if (!order[dof[k]]) {
+			v_first.push_back(value[k]);
+			v_last.push_back(value[k]);
+			order[dof[k]] = (uint32_t)v_first.size();
+		} else {
+			v_last[order[dof[k]] - 1] = value[k];
+		}
+	}
+	const size_t m = v_first.size();
+	void *buf = nullptr;
+	NB_CUDA(cudaMalloc(&buf, (size_t)N * sizeof(uint32_t) + 2 * m * sizeof(double) + 16));
+	double *d_first = (double *)buf, *d_last = d_first + m;
+	uint32_t *d_order = (uint32_t *)(d_last + m);
+	cudaError_t e = cudaMemcpy(d_first, v_first.data(), m * sizeof(double), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(d_last, v_last.data(), m * sizeof(double), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(d_order, order.data(), (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		dirichlet_kernel<<<(N + kBlock - 1) / kBlock, kBlock, 0, c.stream>>>(
+			N, K->d_slice_off, K->d_col, K->d_val, d_F, d_order, d_first, d_last);
+		ctx().launches++;
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(c.stream);
+	cudaFree(buf);
+	if (e != cudaSuccess) {
+		set_error("apply_dirichlet: %s", cudaGetErrorString(e));
+		return NBGPU_ERR_CUDA;
+	}
+	return NBGPU_OK;
+}
+
+int nbgpu_compute_strain(const nbgpu_mesh_t *m, const nbgpu_elem_tables_t *tables, const double *d_disp,
+			 double *d_strain)
+{
+	NB_INIT();
+	NB_ARG(m != nullptr && d_disp != nullptr && d_strain != nullptr);
+	NB_TRY(upload_tables(tables, m->npe));
+	if (m->N_elems == 0)
+		return NBGPU_OK;
+	const int grid = (m->N_elems + kBlock - 1) / kBlock;
+	if (m->npe == 3)
+		strain_kernel<3, 1><<<grid, kBlock, 0, ctx().stream>>>(m->N_elems, m->d_nod, m->d_adj, d_disp,
+								       d_strain);
+	else
+		strain_kernel<4, 4><<<grid, kBlock, 0, ctx().stream>>>(m->N_elems, m->d_nod, m->d_adj, d_disp,
+								       d_strain);
+	NB_LAUNCHED();
+	return NBGPU_OK;
+}
+
+int nbgpu_stress_from_strain(uint32_t N_elems, uint32_t N_gp, const double D[4], const double D_void[4],
+			     const uint8_t *enabled, const double *d_strain, double *d_stress)
+{
+	NB_INIT();
+	NB_ARG(D != nullptr && D_void != nullptr && d_strain != nullptr && d_stress != nullptr);
+	NB_ARG(N_gp == 1 || N_gp == 4);
+	if (N_elems == 0)
+		return NBGPU_OK;
+	Context &c = ctx();
+	uint8_t *d_en = nullptr;
+	if (enabled) {
+		NB_CUDA(cudaMalloc(&d_en, N_elems));
+		NB_CUDA(cudaMemcpyAsync(d_en, enabled, N_elems, cudaMemcpyHostToDevice, c.stream));
+	}
+	const size_t n = (size_t)N_elems * N_gp;
+	stress_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, c.stream>>>(
+		N_elems, N_gp, d_en, D[0], D[1], D[2], D[3], D_void[0], D_void[1], D_void[2], D_void[3],
+		d_strain, d_stress);
+	ctx().launches++;
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess && d_en)
+		e = cudaStreamSynchronize(c.stream);
+	if (d_en)
+		cudaFree(d_en);
+	if (e != cudaSuccess) {
+		set_error("stress_from_strain: %s", cudaGetErrorString(e));
+		return NBGPU_ERR_CUDA;
+	}
+	return NBGPU_OK;
+}
+
+}  // extern "C"

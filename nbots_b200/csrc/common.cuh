@@ -1,0 +1,158 @@
+// common.cuh -- process-wide context, error handling and device helpers shared
+// by every translation unit of libnbgpu.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "nbgpu.h"
+
+namespace nbgpu {
+
+constexpr uint32_t kSliceRows = 32;           // SELL slice height = one warp
+constexpr uint32_t kPadCol = 0xFFFFFFFFu;     // column id of a padding entry
+constexpr int kBlock = 256;                   // threads per CTA of every streaming kernel
+constexpr int kMaxPartialBlocks = 4096;       // upper bound on persistent grid sizes
+
+struct Context {
+	bool ready = false;
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;        // all kernels
+	cudaStream_t copy_stream = nullptr;   // staged uploads
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr;     // nbgpu_timer_*
+	cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+	void *stage[2] = {nullptr, nullptr};  // pinned staging buffers
+	size_t stage_bytes = 0;
+	double *ws = nullptr;                 // Krylov work vectors (grow-only)
+	size_t ws_bytes = 0;
+	double *partials = nullptr;           // [4][kMaxPartialBlocks] reduction partials
+	void *dev_state = nullptr;            // solver scalars (krylov.cu)
+	void *host_state = nullptr;           // pinned mirror
+	uint64_t launches = 0;
+};
+
+Context &ctx();
+int ensure_init();
+void set_error(const char *fmt, ...);
+// pinned staging buffer pair of at least `bytes` each
+int ensure_stage(size_t bytes);
+int ensure_workspace(size_t bytes);
+
+}  // namespace nbgpu
+
+#define NB_CUDA(expr)                                                         \
+	do {                                                                  \
+		cudaError_t nb_e_ = (expr);                                   \
+		if (nb_e_ != cudaSuccess) {                                   \
+			nbgpu::set_error("%s:%d: %s: %s", __FILE__, __LINE__, \
+					 #expr, cudaGetErrorString(nb_e_));   \
+			return NBGPU_ERR_CUDA;                                \
+		}                                                             \
+	} while (0)
+
+#define NB_INIT()                                      \
+	do {                                           \
+		int nb_s_ = nbgpu::ensure_init();      \
+		if (nb_s_ != NBGPU_OK)                 \
+			return nb_s_;                  \
+	} while (0)
+
+#define NB_ARG(cond)                                                            \
+	do {                                                                    \
+		if (!(cond)) {                                                  \
+			nbgpu::set_error("%s:%d: invalid argument: %s",         \
+					 __FILE__, __LINE__, #cond);            \
+			return NBGPU_ERR_ARG;                                   \
+		}                                                               \
+	} while (0)
+
+// count + check a kernel launch
+#define NB_LAUNCHED()                                 \
+	do {                                          \
+		nbgpu::ctx().launches++;              \
+		NB_CUDA(cudaGetLastError());          \
+	} while (0)
+
+#define NB_TRY(expr)                        \
+	do {                                \
+		int nb_s_ = (expr);         \
+		if (nb_s_ != NBGPU_OK)      \
+			return nb_s_;       \
+	} while (0)
+
+// ------------------------------------------------------------------ device --
+#ifdef __CUDACC__
+namespace nbgpu {
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_down_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// Deterministic grid reduction of NV per-thread values.
+//   1. warp shuffle tree, 2. one shared-memory pass per CTA, 3. the CTA that
+//   takes the last ticket sums the per-CTA partials in a fixed order.
+// Returns true (on every thread of that last CTA) with the totals in out[].
+// partials: [NV][gridDim.x]; ticket: zero-initialised counter, self-resetting.
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials,
+					     unsigned int *ticket, double (&out)[NV])
+{
+	__shared__ double sm[NV][kBlock / 32];
+	__shared__ bool is_last;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < NV; k++) {
+		double s = warp_sum(v[k]);
+		if (lane == 0)
+			sm[k][warp] = s;
+	}
+	__syncthreads();
+	if (warp == 0) {
+#pragma unroll
+		for (int k = 0; k < NV; k++) {
+			double s = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
+			s = warp_sum(s);
+			if (lane == 0)
+				partials[k * gridDim.x + blockIdx.x] = s;
+		}
+		if (lane == 0) {
+			__threadfence();
+			unsigned int t = atomicInc(ticket, gridDim.x - 1);
+			is_last = (t == gridDim.x - 1);
+		}
+	}
+	__syncthreads();
+	if (!is_last)
+		return false;
+	__threadfence();
+#pragma unroll
+	for (int k = 0; k < NV; k++) {
+		double s = 0.0;
+		for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock)
+			s += __ldcg(partials + k * gridDim.x + b);
+		s = warp_sum(s);
+		if (lane == 0)
+			sm[k][warp] = s;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < NV; k++) {
+		double s = 0.0;
+#pragma unroll
+		for (int w = 0; w < kBlock / 32; w++)
+			s += sm[k][w];
+		out[k] = s;
+	}
+	return true;
+}
+
+}  // namespace nbgpu
+#endif

@@ -1,0 +1,272 @@
+// context.cu -- process-wide device context, memory helpers, timers.
+#include <cstdarg>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+
+namespace nbgpu {
+
+static thread_local std::string g_error;
+static Context g_ctx;
+
+Context &ctx() { return g_ctx; }
+
+void set_error(const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_error = buf;
+}
+
+static int init_device(int device)
+{
+	Context &c = g_ctx;
+	if (c.ready)
+		return NBGPU_OK;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		// no CPU fallback: the product path needs a CUDA device
+		set_error("no usable CUDA device (%s); libnbgpu has no CPU fallback",
+			  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+		return NBGPU_ERR_CUDA;
+	}
+	if (device < 0) {
+		const char *lr = getenv("LOCAL_RANK");
+		device = lr ? atoi(lr) % count : 0;
+	}
+	NB_ARG(device < count);
+	NB_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	NB_CUDA(cudaGetDeviceProperties(&prop, device));
+	c.device = device;
+	c.sm_count = prop.multiProcessorCount;
+	NB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+	NB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+	NB_CUDA(cudaEventCreate(&c.ev_a));
+	NB_CUDA(cudaEventCreate(&c.ev_b));
+	NB_CUDA(cudaEventCreateWithFlags(&c.ev_stage[0], cudaEventDisableTiming));
+	NB_CUDA(cudaEventCreateWithFlags(&c.ev_stage[1], cudaEventDisableTiming));
+	NB_CUDA(cudaMalloc(&c.partials, sizeof(double) * 4 * kMaxPartialBlocks));
+	c.ready = true;
+	return NBGPU_OK;
+}
+
+int ensure_init()
+{
+	if (g_ctx.ready) {
+		// ctypes / host threads other than the initialising one
+		cudaSetDevice(g_ctx.device);
+		return NBGPU_OK;
+	}
+	return init_device(-1);
+}
+
+int ensure_stage(size_t bytes)
+{
+	Context &c = g_ctx;
+	if (c.stage_bytes >= bytes)
+		return NBGPU_OK;
+	NB_CUDA(cudaStreamSynchronize(c.copy_stream));
+	NB_CUDA(cudaStreamSynchronize(c.stream));
+	for (int i = 0; i < 2; i++) {
+		if (c.stage[i])
+			NB_CUDA(cudaFreeHost(c.stage[i]));
+		c.stage[i] = nullptr;
+	}
+	c.stage_bytes = 0;
+	for (int i = 0; i < 2; i++)
+		NB_CUDA(cudaMallocHost(&c.stage[i], bytes));
+	c.stage_bytes = bytes;
+	return NBGPU_OK;
+}
+
+int ensure_workspace(size_t bytes)
+{
+	Context &c = g_ctx;
+	if (c.ws_bytes >= bytes)
+		return NBGPU_OK;
+	NB_CUDA(cudaStreamSynchronize(c.stream));
+	if (c.ws)
+		NB_CUDA(cudaFree(c.ws));
+	c.ws = nullptr;
+	c.ws_bytes = 0;
+	cudaError_t e = cudaMalloc(&c.ws, bytes);
+	if (e != cudaSuccess) {
+		set_error("workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+		cudaGetLastError();
+		return NBGPU_ERR_NOMEM;
+	}
+	c.ws_bytes = bytes;
+	return NBGPU_OK;
+}
+
+}  // namespace nbgpu
+
+using namespace nbgpu;
+
+extern "C" {
+
+int nbgpu_init(int device)
+{
+	if (g_ctx.ready) {
+		if (device >= 0 && device != g_ctx.device) {
+			set_error("already bound to device %d", g_ctx.device);
+			return NBGPU_ERR_ARG;
+		}
+		return NBGPU_OK;
+	}
+	return init_device(device);
+}
+
+int nbgpu_finalize(void)
+{
+	Context &c = g_ctx;
+	if (!c.ready)
+		return NBGPU_OK;
+	cudaSetDevice(c.device);
+	cudaStreamSynchronize(c.stream);
+	cudaStreamSynchronize(c.copy_stream);
+	for (int i = 0; i < 2; i++) {
+		if (c.stage[i])
+			cudaFreeHost(c.stage[i]);
+		cudaEventDestroy(c.ev_stage[i]);
+	}
+	if (c.ws)
+		cudaFree(c.ws);
+	if (c.partials)
+		cudaFree(c.partials);
+	if (c.dev_state)
+		cudaFree(c.dev_state);
+	if (c.host_state)
+		cudaFreeHost(c.host_state);
+	cudaEventDestroy(c.ev_a);
+	cudaEventDestroy(c.ev_b);
+	cudaStreamDestroy(c.stream);
+	cudaStreamDestroy(c.copy_stream);
+	uint64_t launches = c.launches;
+	c = Context();
+	c.launches = launches;
+	return NBGPU_OK;
+}
+
+int nbgpu_device_count(void)
+{
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return count;
+}
+
+int nbgpu_sync(void)
+{
+	NB_INIT();
+	NB_CUDA(cudaStreamSynchronize(g_ctx.copy_stream));
+	NB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+	return NBGPU_OK;
+}
+
+const char *nbgpu_last_error(void) { return g_error.c_str(); }
+
+void *nbgpu_stream(void)
+{
+	if (ensure_init() != NBGPU_OK)
+		return nullptr;
+	return (void *)g_ctx.stream;
+}
+
+uint64_t nbgpu_launch_count(void) { return g_ctx.launches; }
+
+int nbgpu_malloc(void **d_ptr, size_t bytes)
+{
+	NB_INIT();
+	NB_ARG(d_ptr != nullptr);
+	cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+	if (e != cudaSuccess) {
+		set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+		cudaGetLastError();
+		return NBGPU_ERR_NOMEM;
+	}
+	return NBGPU_OK;
+}
+
+int nbgpu_free(void *d_ptr)
+{
+	NB_INIT();
+	if (d_ptr) {
+		NB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+		NB_CUDA(cudaFree(d_ptr));
+	}
+	return NBGPU_OK;
+}
+
+int nbgpu_memset(void *d_ptr, int byte, size_t bytes)
+{
+	NB_INIT();
+	NB_CUDA(cudaMemsetAsync(d_ptr, byte, bytes, g_ctx.stream));
+	return NBGPU_OK;
+}
+
+int nbgpu_copy_h2d(void *d_dst, const void *src, size_t bytes)
+{
+	NB_INIT();
+	NB_CUDA(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+	NB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+	return NBGPU_OK;
+}
+
+int nbgpu_copy_d2h(void *dst, const void *d_src, size_t bytes)
+{
+	NB_INIT();
+	NB_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+	NB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+	return NBGPU_OK;
+}
+
+int nbgpu_copy_d2d(void *d_dst, const void *d_src, size_t bytes)
+{
+	NB_INIT();
+	NB_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
+	return NBGPU_OK;
+}
+
+int nbgpu_host_alloc(void **ptr, size_t bytes)
+{
+	NB_INIT();
+	NB_ARG(ptr != nullptr);
+	NB_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+	return NBGPU_OK;
+}
+
+int nbgpu_host_free(void *ptr)
+{
+	NB_INIT();
+	if (ptr)
+		NB_CUDA(cudaFreeHost(ptr));
+	return NBGPU_OK;
+}
+
+int nbgpu_timer_start(void)
+{
+	NB_INIT();
+	NB_CUDA(cudaEventRecord(g_ctx.ev_a, g_ctx.stream));
+	return NBGPU_OK;
+}
+
+int nbgpu_timer_stop(float *elapsed_ms)
+{
+	NB_INIT();
+	NB_CUDA(cudaEventRecord(g_ctx.ev_b, g_ctx.stream));
+	NB_CUDA(cudaEventSynchronize(g_ctx.ev_b));
+	if (elapsed_ms)
+		NB_CUDA(cudaEventElapsedTime(elapsed_ms, g_ctx.ev_a, g_ctx.ev_b));
+	return NBGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+// matrix.cu -- nb_sparse_t -> SELL-32 in HBM: creation, value import/export.
+// Reference: struct nb_sparse_s (sources/nb/solver_bot/sparse/sparse_struct.h:6-11),
+// nb_sparse_create (sparse.c:20-60), nb_sparse_reset (sparse.c:127-132).
+#include <cstring>
+#include <algorithm>
+
+#include "matrix.cuh"
+
+using namespace nbgpu;
+
+namespace {
+
+constexpr size_t kStageBytes = size_t(32) << 20;   // per pinned staging buffer
+
+// One warp per slice: transpose CSR rows into the slice's column-major block.
+// csr_val == nullptr writes zero values; sell_col == nullptr leaves the
+// pattern untouched (value-only import).  *bad is raised if a row's columns
+// are not strictly ascending or out of range (the reference's invariant after
+// nb_qsort, sparse.c:55).
+__global__ void __launch_bounds__(kBlock)
+csr_to_sell_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
+		   const uint32_t *__restrict__ csr_col, const double *__restrict__ csr_val,
+		   const uint32_t *__restrict__ slice_off, uint32_t *__restrict__ sell_col,
+		   double *__restrict__ sell_val, int *bad)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
+		const uint32_t row = s * kSliceRows + lane;
+		const uint32_t off = slice_off[s], width = slice_off[s + 1] - off;
+		uint64_t base = 0;
+		uint32_t len = 0;
+		if (row < N) {
+			base = row_ptr[row];
+			len = (uint32_t)(row_ptr[row + 1] - base);
+		}
+		uint32_t prev = 0;
+		for (uint32_t j = 0; j < width; j++) {
+			const size_t idx = ((size_t)off + j) * kSliceRows + lane;
+			if (j < len) {
+				if (sell_col) {
+					uint32_t c = csr_col[base + j];
+					if (c >= N || (j > 0 && c <= prev))
+						*bad = 1;
+					prev = c;
+					sell_col[idx] = c;
+				}
+				sell_val[idx] = csr_val ? csr_val[base + j] : 0.0;
+			} else {
+				if (sell_col)
+					sell_col[idx] = kPadCol;
+				sell_val[idx] = 0.0;
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kBlock)
+sell_to_csr_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
+		   const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ sell_col,
+		   const double *__restrict__ sell_val, uint32_t *__restrict__ csr_col,
+		   double *__restrict__ csr_val)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
+		const uint32_t row = s * kSliceRows + lane;
+		if (row >= N)
+			continue;
+		const uint32_t off = slice_off[s];
+		const uint64_t base = row_ptr[row];
+		const uint32_t len = (uint32_t)(row_ptr[row + 1] - base);
+		for (uint32_t j = 0; j < len; j++) {
+			const size_t idx = ((size_t)off + j) * kSliceRows + lane;
+			if (csr_col)
+				csr_col[base + j] = sell_col[idx];
+			if (csr_val)
+				csr_val[base + j] = sell_val[idx];
+		}
+	}
+}
+
+int grid_for_slices(uint32_t n_slices)
+{
+	int64_t want = ((int64_t)n_slices * 32 + kBlock - 1) / kBlock;
+	int64_t cap = (int64_t)ctx().sm_count * 8;
+	return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+// Host -> device copy of `count` elements of T that the caller can only hand
+// over piecewise: fill(chunk, first, last, dst) must write elements [first,last) of
+// the logical array to dst[0..last-first).  Double-buffered pinned staging on
+// the copy stream, so gathering chunk k+1 overlaps the DMA of chunk k.
+template <typename T, typename Fill>
+int upload_staged(T *d_dst, size_t count, const std::vector<size_t> &cuts, Fill fill)
+{
+	Context &c = ctx();
+	NB_TRY(ensure_stage(kStageBytes));
+	int buf = 0;
+	for (size_t k = 0; k + 1 < cuts.size(); k++) {
+		size_t first = cuts[k], last = cuts[k + 1];
+		if (last == first)
+			continue;
+		NB_CUDA(cudaEventSynchronize(c.ev_stage[buf]));
+		fill(k, first, last, (T *)c.stage[buf]);
+		NB_CUDA(cudaMemcpyAsync(d_dst + first, c.stage[buf], (last - first) * sizeof(T),
+					cudaMemcpyHostToDevice, c.copy_stream));
+		NB_CUDA(cudaEventRecord(c.ev_stage[buf], c.copy_stream));
+		buf ^= 1;
+	}
+	(void)count;
+	return NBGPU_OK;
+}
+
+// element cuts of at most `max_elems` that fall on row boundaries
+std::vector<size_t> row_cuts(const std::vector<uint64_t> &row_ptr, size_t max_elems,
+			     std::vector<uint32_t> *cut_rows)
+{
+	std::vector<size_t> cuts{0};
+	cut_rows->assign(1, 0);
+	const uint32_t N = (uint32_t)row_ptr.size() - 1;
+	uint32_t r = 0;
+	while (r < N) {
+		uint64_t limit = row_ptr[r] + max_elems;
+		uint32_t hi = (uint32_t)(std::upper_bound(row_ptr.begin() + r, row_ptr.end(), limit) -
+					 row_ptr.begin()) - 1;
+		if (hi <= r)
+			hi = r + 1;   // a single row longer than the buffer cannot happen (len <= 2^32)
+		cuts.push_back(row_ptr[hi]);
+		cut_rows->push_back(hi);
+		r = hi;
+	}
+	return cuts;
+}
+
+std::vector<size_t> flat_cuts(size_t count, size_t max_elems)
+{
+	std::vector<size_t> cuts{0};
+	for (size_t p = 0; p < count;) {
+		p = std::min(count, p + max_elems);
+		cuts.push_back(p);
+	}
+	return cuts;
+}
+
+template <typename T>
+int upload_flat(T *d_dst, const T *src, size_t count)
+{
+	auto cuts = flat_cuts(count, kStageBytes / sizeof(T));
+	return upload_staged<T>(d_dst, count, cuts, [&](size_t, size_t first, size_t last, T *dst) {
+		const size_t n = last - first;
+		const size_t piece = size_t(1) << 18;
+#pragma omp parallel for schedule(static)
+		for (int64_t p = 0; p < (int64_t)((n + piece - 1) / piece); p++) {
+			size_t b = (size_t)p * piece, e = std::min(n, b + piece);
+			memcpy(dst + b, src + first + b, (e - b) * sizeof(T));
+		}
+	});
+}
+
+template <typename T>
+int upload_rows(T *d_dst, T *const *rows, const std::vector<uint64_t> &row_ptr)
+{
+	std::vector<uint32_t> cut_rows;
+	auto cuts = row_cuts(row_ptr, kStageBytes / sizeof(T), &cut_rows);
+	return upload_staged<T>(d_dst, row_ptr.back(), cuts, [&](size_t k, size_t first, size_t, T *dst) {
+		const uint32_t r0 = cut_rows[k], r1 = cut_rows[k + 1];
+#pragma omp parallel for schedule(static)
+		for (int64_t r = r0; r < (int64_t)r1; r++)
+			memcpy(dst + (row_ptr[r] - first), rows[r],
+			       (row_ptr[r + 1] - row_ptr[r]) * sizeof(T));
+	});
+}
+
+struct DeviceTemp {
+	void *p = nullptr;
+	~DeviceTemp()
+	{
+		if (p)
+			cudaFree(p);
+	}
+	int alloc(size_t bytes)
+	{
+		cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+		if (e != cudaSuccess) {
+			set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+			cudaGetLastError();
+			p = nullptr;
+			return NBGPU_ERR_NOMEM;
+		}
+		return NBGPU_OK;
+	}
+};
+
+int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
+{
+	A->N = N;
+	A->h_rows_size.assign(rows_size, rows_size + N);
+	A->h_row_ptr.resize((size_t)N + 1);
+	A->h_row_ptr[0] = 0;
+	for (uint32_t i = 0; i < N; i++)
+		A->h_row_ptr[i + 1] = A->h_row_ptr[i] + rows_size[i];
+	A->nnz = A->h_row_ptr[N];
+	A->n_slices = (N + kSliceRows - 1) / kSliceRows;
+	std::vector<uint32_t> off((size_t)A->n_slices + 1);
+	uint64_t units = 0;
+	A->max_width = 0;
+	for (uint32_t s = 0; s < A->n_slices; s++) {
+		off[s] = (uint32_t)units;
+		uint32_t w = 0;
+		const uint32_t r1 = std::min<uint64_t>(N, (uint64_t)(s + 1) * kSliceRows);
+		for (uint32_t r = s * kSliceRows; r < r1; r++)
+			w = std::max(w, rows_size[r]);
+		A->max_width = std::max(A->max_width, w);
+		units += w;
+		if (units > 0xFFFFFFFFull) {
+			set_error("matrix too large for 32-bit slice offsets");
+			return NBGPU_ERR_ARG;
+		}
+	}
+	off[A->n_slices] = (uint32_t)units;
+	A->stored = units * kSliceRows;
+	NB_CUDA(cudaMalloc(&A->d_slice_off, off.size() * sizeof(uint32_t)));
+	NB_CUDA(cudaMemcpyAsync(A->d_slice_off, off.data(), off.size() * sizeof(uint32_t),
+				cudaMemcpyHostToDevice, ctx().stream));
+	NB_CUDA(cudaStreamSynchronize(ctx().stream));   // `off` goes out of scope
+	cudaError_t e = cudaMalloc(&A->d_val, std::max<size_t>(1, A->stored) * sizeof(double));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&A->d_col, std::max<size_t>(1, A->stored) * sizeof(uint32_t));
+	if (e != cudaSuccess) {
+		set_error("matrix of %llu stored entries: %s", (unsigned long long)A->stored,
+			  cudaGetErrorString(e));
+		cudaGetLastError();
+		return NBGPU_ERR_NOMEM;
+	}
+	return NBGPU_OK;
+}
+
+// Common tail of the two constructors / value setters: CSR arrays already in
+// device temporaries (d_cols may be null = keep pattern, d_vals may be null =
+// zeros) -> SELL.
+int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
+{
+	Context &c = ctx();
+	DeviceTemp rp, bad;
+	NB_TRY(rp.alloc(A->h_row_ptr.size() * sizeof(uint64_t)));
+	NB_TRY(bad.alloc(sizeof(int)));
+	NB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), c.stream));
+	NB_CUDA(cudaMemcpyAsync(rp.p, A->h_row_ptr.data(), A->h_row_ptr.size() * sizeof(uint64_t),
+				cudaMemcpyHostToDevice, c.stream));
+	NB_CUDA(cudaStreamSynchronize(c.copy_stream));   // staged uploads have landed
+	if (A->n_slices) {
+		csr_to_sell_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
+			A->N, A->n_slices, (const uint64_t *)rp.p, d_cols, d_vals, A->d_slice_off,
+			d_cols ? A->d_col : nullptr, A->d_val, (int *)bad.p);
+		NB_LAUNCHED();
+	}
+	int h_bad = 0;
+	NB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	NB_CUDA(cudaStreamSynchronize(c.stream));
+	if (h_bad) {
+		set_error("row columns must be strictly ascending and < N (nb_sparse_create invariant)");
+		return NBGPU_ERR_ARG;
+	}
+	return NBGPU_OK;
+}
+
+int convert_out(const nbgpu_matrix_t *A, uint32_t *d_cols, double *d_vals)
+{
+	Context &c = ctx();
+	DeviceTemp rp;
+	NB_TRY(rp.alloc(A->h_row_ptr.size() * sizeof(uint64_t)));
+	NB_CUDA(cudaMemcpyAsync(rp.p, A->h_row_ptr.data(), A->h_row_ptr.size() * sizeof(uint64_t),
+				cudaMemcpyHostToDevice, c.stream));
+	if (A->n_slices) {
+		sell_to_csr_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
+			A->N, A->n_slices, (const uint64_t *)rp.p, A->d_slice_off, A->d_col, A->d_val,
+			d_cols, d_vals);
+		NB_LAUNCHED();
+	}
+	NB_CUDA(cudaStreamSynchronize(c.stream));
+	return NBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nbgpu_matrix_destroy(nbgpu_matrix_t *A)
+{
+	if (!A)
+		return NBGPU_OK;
+	if (ctx().ready) {
+		cudaSetDevice(ctx().device);
+		cudaStreamSynchronize(ctx().stream);
+		cudaFree(A->d_slice_off);
+		cudaFree(A->d_val);
+		cudaFree(A->d_col);
+	}
+	delete A;
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_create_from_csr(uint32_t N, const uint32_t *rows_size, const uint32_t *cols,
+				 const double *vals, nbgpu_matrix_t **out)
+{
+	NB_INIT();
+	NB_ARG(out != nullptr && (N == 0 || (rows_size != nullptr && cols != nullptr)));
+	nbgpu_matrix_t *A = new nbgpu_matrix_t();
+	int st = build_layout(A, N, rows_size);
+	DeviceTemp dc, dv;
+	if (st == NBGPU_OK)
+		st = dc.alloc(A->nnz * sizeof(uint32_t));
+	if (st == NBGPU_OK && vals)
+		st = dv.alloc(A->nnz * sizeof(double));
+	if (st == NBGPU_OK)
+		st = upload_flat<uint32_t>((uint32_t *)dc.p, cols, A->nnz);
+	if (st == NBGPU_OK && vals)
+		st = upload_flat<double>((double *)dv.p, vals, A->nnz);
+	if (st == NBGPU_OK)
+		st = convert_in(A, (const uint32_t *)dc.p, vals ? (const double *)dv.p : nullptr);
+	if (st != NBGPU_OK) {
+		nbgpu_matrix_destroy(A);
+		return st;
+	}
+	*out = A;
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_create_from_rows(uint32_t N, const uint32_t *rows_size, uint32_t *const *rows_index,
+				  double *const *rows_values, nbgpu_matrix_t **out)
+{
+	NB_INIT();
+	NB_ARG(out != nullptr && (N == 0 || (rows_size != nullptr && rows_index != nullptr)));
+	nbgpu_matrix_t *A = new nbgpu_matrix_t();
+	int st = build_layout(A, N, rows_size);
+	DeviceTemp dc, dv;
+	if (st == NBGPU_OK)
+		st = dc.alloc(A->nnz * sizeof(uint32_t));
+	if (st == NBGPU_OK && rows_values)
+		st = dv.alloc(A->nnz * sizeof(double));
+	if (st == NBGPU_OK)
+		st = upload_rows<uint32_t>((uint32_t *)dc.p, rows_index, A->h_row_ptr);
+	if (st == NBGPU_OK && rows_values)
+		st = upload_rows<double>((double *)dv.p, rows_values, A->h_row_ptr);
+	if (st == NBGPU_OK)
+		st = convert_in(A, (const uint32_t *)dc.p, rows_values ? (const double *)dv.p : nullptr);
+	if (st != NBGPU_OK) {
+		nbgpu_matrix_destroy(A);
+		return st;
+	}
+	*out = A;
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_info(const nbgpu_matrix_t *A, uint32_t *N, uint64_t *nnz, uint32_t *n_slices,
+		      uint64_t *stored_entries)
+{
+	NB_ARG(A != nullptr);
+	if (N)
+		*N = A->N;
+	if (nnz)
+		*nnz = A->nnz;
+	if (n_slices)
+		*n_slices = A->n_slices;
+	if (stored_entries)
+		*stored_entries = A->stored;
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_set_values_csr(nbgpu_matrix_t *A, const double *vals)
+{
+	NB_INIT();
+	NB_ARG(A != nullptr && vals != nullptr);
+	DeviceTemp dv;
+	NB_TRY(dv.alloc(A->nnz * sizeof(double)));
+	NB_TRY(upload_flat<double>((double *)dv.p, vals, A->nnz));
+	return convert_in(A, nullptr, (const double *)dv.p);
+}
+
+int nbgpu_matrix_set_values_rows(nbgpu_matrix_t *A, double *const *rows_values)
+{
+	NB_INIT();
+	NB_ARG(A != nullptr && rows_values != nullptr);
+	DeviceTemp dv;
+	NB_TRY(dv.alloc(A->nnz * sizeof(double)));
+	NB_TRY(upload_rows<double>((double *)dv.p, rows_values, A->h_row_ptr));
+	return convert_in(A, nullptr, (const double *)dv.p);
+}
+
+int nbgpu_matrix_get_values_csr(const nbgpu_matrix_t *A, double *vals)
+{
+	NB_INIT();
+	NB_ARG(A != nullptr && vals != nullptr);
+	DeviceTemp dv;
+	NB_TRY(dv.alloc(A->nnz * sizeof(double)));
+	NB_TRY(convert_out(A, nullptr, (double *)dv.p));
+	NB_CUDA(cudaMemcpy(vals, dv.p, A->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_get_values_rows(const nbgpu_matrix_t *A, double *const *rows_values)
+{
+	NB_INIT();
+	NB_ARG(A != nullptr && rows_values != nullptr);
+	std::vector<double> flat(A->nnz);
+	NB_TRY(nbgpu_matrix_get_values_csr(A, flat.data()));
+#pragma omp parallel for schedule(static)
+	for (int64_t r = 0; r < (int64_t)A->N; r++)
+		memcpy(rows_values[r], flat.data() + A->h_row_ptr[r],
+		       (A->h_row_ptr[r + 1] - A->h_row_ptr[r]) * sizeof(double));
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_get_pattern_csr(const nbgpu_matrix_t *A, uint32_t *rows_size, uint32_t *cols)
+{
+	NB_INIT();
+	NB_ARG(A != nullptr);
+	if (rows_size)
+		memcpy(rows_size, A->h_rows_size.data(), (size_t)A->N * sizeof(uint32_t));
+	if (cols) {
+		DeviceTemp dc;
+		NB_TRY(dc.alloc(A->nnz * sizeof(uint32_t)));
+		NB_TRY(convert_out(A, (uint32_t *)dc.p, nullptr));
+		NB_CUDA(cudaMemcpy(cols, dc.p, A->nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	}
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_reset(nbgpu_matrix_t *A)
+{
+	NB_INIT();
+	NB_ARG(A != nullptr);
+	NB_CUDA(cudaMemsetAsync(A->d_val, 0, A->stored * sizeof(double), ctx().stream));
+	return NBGPU_OK;
+}
+
+}  // extern "C"

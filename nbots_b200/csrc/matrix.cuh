@@ -1,0 +1,39 @@
+// matrix.cuh -- device-resident form of the reference's nb_sparse_t.
+//
+// Layout in HBM (SELL-32): rows are grouped in slices of 32 consecutive rows
+// (one warp).  Slice s has width w_s = max row length in the slice and stores
+// its entries column-major: entry j of row 32*s + lane sits at
+//     (slice_off[s] + j) * 32 + lane
+// so that a warp reading "entry j of its 32 rows" issues one fully coalesced
+// 256-byte (values) / 128-byte (column ids) request.  Rows shorter than w_s
+// are padded with value 0 and column id kPadCol; the padding is skipped
+// arithmetically (never added), so a row sum is exactly the reference's
+// ascending-column sum (sources/nb/solver_bot/sparse/sparse.c:405-414).
+// slice_off is in units of 32 entries, which keeps it 32-bit up to 2^37 nnz.
+#pragma once
+
+#include "common.cuh"
+
+struct nbgpu_matrix_s {
+	uint32_t N = 0;
+	uint64_t nnz = 0;
+	uint32_t n_slices = 0;
+	uint64_t stored = 0;                  // padded entry count = 32 * slice_off[n_slices]
+	uint32_t max_width = 0;
+	uint32_t *d_slice_off = nullptr;      // [n_slices + 1]
+	double *d_val = nullptr;              // [stored]
+	uint32_t *d_col = nullptr;            // [stored]
+	std::vector<uint32_t> h_rows_size;    // host copy of the pattern's row lengths
+	std::vector<uint64_t> h_row_ptr;      // CSR offsets (host), for value import/export
+};
+
+namespace nbgpu {
+
+// entry index of (row, j) in the SELL arrays
+__host__ __device__ __forceinline__ size_t sell_index(const uint32_t *slice_off,
+						       uint32_t row, uint32_t j)
+{
+	return ((size_t)slice_off[row >> 5] + j) * kSliceRows + (row & 31);
+}
+
+}  // namespace nbgpu

@@ -1,0 +1,477 @@
+/*
+ * nb_shim.c -- the reference-named entry points of the hot path, implemented
+ * on top of the C ABI in include/nbgpu.h.  This is the "host side stays in C
+ * behind the existing solver_bot/pde_bot entry points" layer: the functions
+ * below have EXACTLY the reference's names, argument lists and return codes,
+ * so a program linked against libnbots picks them up by ordinary symbol
+ * interposition (link libnbots_b200.so before libnbots, or LD_PRELOAD it; see
+ * INTEGRATION.md).
+ *
+ *   nb_sparse_solve_CG_precond_Jacobi   headers/nb/solver_bot/sparse/solvers/cg_precond_jacobi.h:8-15
+ *   nb_sparse_solve_conjugate_gradient  headers/nb/solver_bot/sparse/solvers/conjugate_gradient.h:8-15
+ *   nb_sparse_multiply_vector           headers/nb/solver_bot/sparse/sparse.h:54-55
+ *   pipeline_assemble_system            sources/nb/pde_bot/finite_element/solid_mechanics/pipeline.h:21-30
+ *   nb_fem_compute_2D_Solid_Mechanics   headers/nb/pde_bot/finite_element/solid_mechanics/static_elasticity2D.h:13-24
+ *
+ * The reference passes opaque objects (nb_sparse_t, nb_mesh2D_t, nb_fem_elem_t,
+ * nb_material_t, nb_bcond_t).  nb_sparse_t is read through an ABI mirror of its
+ * four-field struct, exactly as the reference's own solvers do through their
+ * private header (cg_precond_jacobi.c:11).  Everything else is read through
+ * the reference's PUBLIC accessor functions, looked up in the running process
+ * with dlsym so that this library carries no link-time dependency on libnbots.
+ *
+ * No reference code is contained here; only its interface is mirrored.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nbgpu.h"
+
+/* ABI mirror of struct nb_sparse_s (sources/nb/solver_bot/sparse/sparse_struct.h:6-11) */
+typedef struct nb_sparse_s {
+	double **rows_values;
+	uint32_t **rows_index;
+	uint32_t *rows_size;
+	uint32_t N;
+} nb_sparse_t;
+
+/* opaque reference types */
+typedef struct nb_mesh2D_s nb_mesh2D_t;
+typedef struct nb_fem_elem_s nb_fem_elem_t;
+typedef struct nb_material_s nb_material_t;
+typedef struct nb_bcond_s nb_bcond_t;
+typedef struct nb_bcond_iter_s nb_bcond_iter_t;
+
+/* headers/nb/pde_bot/common_solid_mechanics/analysis2D.h */
+typedef int nb_analysis2D_t;
+typedef struct {
+	double thickness;
+	double revolution_axe;
+	char revolution_coordinate;
+} nb_analysis2D_params;
+
+static void report(const char *who, int status)
+{
+	if (status >= 10)
+		fprintf(stderr, "nbots_b200: %s failed (%d): %s\n", who, status, nbgpu_last_error());
+}
+
+/* ----------------------------------------------------------- solver bot -- */
+
+static int solve(const nb_sparse_t *A, const double *b, double *x, uint32_t max_iter, double tolerance,
+		 uint32_t *niter_performed, double *tolerance_reached, int jacobi)
+{
+	nbgpu_matrix_t *M = NULL;
+	int st = nbgpu_matrix_create_from_rows(A->N, A->rows_size, A->rows_index, A->rows_values, &M);
+	if (st == NBGPU_OK)
+		st = jacobi ? nbgpu_pcg_jacobi_host(M, b, x, max_iter, tolerance, niter_performed,
+						    tolerance_reached)
+			    : nbgpu_cg_host(M, b, x, max_iter, tolerance, niter_performed, tolerance_reached);
+	nbgpu_matrix_destroy(M);
+	report(jacobi ? "nb_sparse_solve_CG_precond_Jacobi" : "nb_sparse_solve_conjugate_gradient", st);
+	return st;
+}
+
+/* omp_parallel_threads is the reference's per-call OpenMP hint; the device
+ * decides its own parallelism, the argument is accepted and ignored. */
+int nb_sparse_solve_CG_precond_Jacobi(const nb_sparse_t *const A, const double *const b, double *_x,
+				      uint32_t max_iter, double tolerance, uint32_t *niter_performed,
+				      double *tolerance_reached, uint32_t omp_parallel_threads)
+{
+	(void)omp_parallel_threads;
+	return solve(A, b, _x, max_iter, tolerance, niter_performed, tolerance_reached, 1);
+}
+
+int nb_sparse_solve_conjugate_gradient(const nb_sparse_t *const A, const double *const b, double *_x,
+				       uint32_t max_iter, double tolerance, uint32_t *niter_performed,
+				       double *tolerance_reached, uint32_t omp_parallel_threads)
+{
+	(void)omp_parallel_threads;
+	return solve(A, b, _x, max_iter, tolerance, niter_performed, tolerance_reached, 0);
+}
+
+void nb_sparse_multiply_vector(const nb_sparse_t *A, const double *in, double *out,
+			       uint32_t omp_parallel_threads)
+{
+	(void)omp_parallel_threads;
+	nbgpu_matrix_t *M = NULL;
+	int st = nbgpu_matrix_create_from_rows(A->N, A->rows_size, A->rows_index, A->rows_values, &M);
+	if (st == NBGPU_OK)
+		st = nbgpu_spmv_host(M, in, out);
+	nbgpu_matrix_destroy(M);
+	if (st != NBGPU_OK) {
+		/* the reference signature is void: a device failure cannot be reported, so it is fatal */
+		report("nb_sparse_multiply_vector", st);
+		exit(1);
+	}
+}
+
+/* -------------------------------------------------------------- PDE bot -- */
+
+/* public accessors of the reference, resolved at first use */
+static struct {
+	int ready;
+	uint32_t (*mesh_N_nodes)(const nb_mesh2D_t *);
+	uint32_t (*mesh_N_edges)(const nb_mesh2D_t *);
+	uint32_t (*mesh_N_elems)(const nb_mesh2D_t *);
+	uint32_t (*mesh_N_invtx)(const nb_mesh2D_t *);
+	uint32_t (*mesh_N_insgm)(const nb_mesh2D_t *);
+	double (*node_x)(const nb_mesh2D_t *, uint32_t);
+	double (*node_y)(const nb_mesh2D_t *, uint32_t);
+	uint32_t (*edge_1n)(const nb_mesh2D_t *, uint32_t);
+	uint32_t (*edge_2n)(const nb_mesh2D_t *, uint32_t);
+	uint32_t (*elem_adj)(const nb_mesh2D_t *, uint32_t, uint8_t);
+	uint32_t (*invtx)(const nb_mesh2D_t *, uint32_t);
+	uint32_t (*insgm_N_nodes)(const nb_mesh2D_t *, uint32_t);
+	uint32_t (*insgm_node)(const nb_mesh2D_t *, uint32_t, uint32_t);
+	double (*insgm_length)(const nb_mesh2D_t *, uint32_t);
+	double (*insgm_sub_length)(const nb_mesh2D_t *, uint32_t, uint32_t);
+	uint8_t (*elem_N_gp)(const nb_fem_elem_t *);
+	uint8_t (*elem_N_nodes)(const nb_fem_elem_t *);
+	double (*elem_w)(const nb_fem_elem_t *, uint8_t);
+	double (*elem_Ni)(const nb_fem_elem_t *, uint8_t, uint8_t);
+	double (*elem_dpsi)(const nb_fem_elem_t *, uint8_t, uint8_t);
+	double (*elem_deta)(const nb_fem_elem_t *, uint8_t, uint8_t);
+	double (*mat_density)(const nb_material_t *);
+	void (*constitutive)(double D[4], const nb_material_t *, nb_analysis2D_t);
+	uint8_t (*bc_N_dof)(const nb_bcond_t *);
+	uint16_t (*it_memsize)(void);
+	void (*it_init)(void *);
+	void (*it_finish)(void *);
+	void (*it_set)(nb_bcond_iter_t *, const nb_bcond_t *, int, int);
+	bool (*it_more)(const nb_bcond_iter_t *);
+	void (*it_next)(nb_bcond_iter_t *);
+	uint32_t (*it_id)(const nb_bcond_iter_t *);
+	bool (*it_mask)(const nb_bcond_iter_t *, uint8_t);
+	bool (*it_is_fn)(const nb_bcond_iter_t *);
+	void (*it_val)(const nb_bcond_iter_t *, uint8_t, double *, double, double[]);
+} R;
+
+static void *need(const char *name)
+{
+	void *p = dlsym(RTLD_DEFAULT, name);
+	if (!p) {
+		fprintf(stderr, "nbots_b200: the FEM shims need libnbots in the process "
+			"(symbol %s not found)\n", name);
+		exit(1);
+	}
+	return p;
+}
+
+static void resolve(void)
+{
+	if (R.ready)
+		return;
+	*(void **)&R.mesh_N_nodes = need("nb_mesh2D_get_N_nodes");
+	*(void **)&R.mesh_N_edges = need("nb_mesh2D_get_N_edges");
+	*(void **)&R.mesh_N_elems = need("nb_mesh2D_get_N_elems");
+	*(void **)&R.mesh_N_invtx = need("nb_mesh2D_get_N_invtx");
+	*(void **)&R.mesh_N_insgm = need("nb_mesh2D_get_N_insgm");
+	*(void **)&R.node_x = need("nb_mesh2D_node_get_x");
+	*(void **)&R.node_y = need("nb_mesh2D_node_get_y");
+	*(void **)&R.edge_1n = need("nb_mesh2D_edge_get_1n");
+	*(void **)&R.edge_2n = need("nb_mesh2D_edge_get_2n");
+	*(void **)&R.elem_adj = need("nb_mesh2D_elem_get_adj");
+	*(void **)&R.invtx = need("nb_mesh2D_get_invtx");
+	*(void **)&R.insgm_N_nodes = need("nb_mesh2D_insgm_get_N_nodes");
+	*(void **)&R.insgm_node = need("nb_mesh2D_insgm_get_node");
+	*(void **)&R.insgm_length = need("nb_mesh2D_insgm_get_length");
+	*(void **)&R.insgm_sub_length = need("nb_mesh2D_insgm_subsgm_get_length");
+	*(void **)&R.elem_N_gp = need("nb_fem_elem_get_N_gpoints");
+	*(void **)&R.elem_N_nodes = need("nb_fem_elem_get_N_nodes");
+	*(void **)&R.elem_w = need("nb_fem_elem_weight_gp");
+	*(void **)&R.elem_Ni = need("nb_fem_elem_Ni");
+	*(void **)&R.elem_dpsi = need("nb_fem_elem_dNi_dpsi");
+	*(void **)&R.elem_deta = need("nb_fem_elem_dNi_deta");
+	*(void **)&R.mat_density = need("nb_material_get_density");
+	*(void **)&R.constitutive = need("nb_pde_get_constitutive_matrix");
+	*(void **)&R.bc_N_dof = need("nb_bcond_get_N_dof");
+	*(void **)&R.it_memsize = need("nb_bcond_iter_get_memsize");
+	*(void **)&R.it_init = need("nb_bcond_iter_init");
+	*(void **)&R.it_finish = need("nb_bcond_iter_finish");
+	*(void **)&R.it_set = need("nb_bcond_iter_set_conditions");
+	*(void **)&R.it_more = need("nb_bcond_iter_has_more");
+	*(void **)&R.it_next = need("nb_bcond_iter_go_next");
+	*(void **)&R.it_id = need("nb_bcond_iter_get_id");
+	*(void **)&R.it_mask = need("nb_bcond_iter_get_mask");
+	*(void **)&R.it_is_fn = need("nb_bcond_iter_val_is_function");
+	*(void **)&R.it_val = need("nb_bcond_iter_get_val");
+	R.ready = 1;
+}
+
+typedef struct {
+	nbgpu_mesh_desc_t d;
+	double *nod;
+	uint32_t *adj, *edg, *vtx, *sgm_sizes, *sgm_nodes;
+} flat_mesh_t;
+
+static int flatten_mesh(const nb_mesh2D_t *part, uint32_t npe, int with_topology, flat_mesh_t *m)
+{
+	memset(m, 0, sizeof(*m));
+	uint32_t N_nod = R.mesh_N_nodes(part), N_el = R.mesh_N_elems(part);
+	m->nod = malloc((2 * (size_t)N_nod + 1) * sizeof(double));
+	m->adj = malloc(((size_t)npe * N_el + 1) * sizeof(uint32_t));
+	if (!m->nod || !m->adj)
+		return NBGPU_ERR_NOMEM;
+	for (uint32_t i = 0; i < N_nod; i++) {
+		m->nod[2 * i] = R.node_x(part, i);
+		m->nod[2 * i + 1] = R.node_y(part, i);
+	}
+	for (uint32_t e = 0; e < N_el; e++)
+		for (uint32_t j = 0; j < npe; j++)
+			m->adj[(size_t)npe * e + j] = R.elem_adj(part, e, (uint8_t)j);
+	m->d.N_nod = N_nod;
+	m->d.nod = m->nod;
+	m->d.N_elems = N_el;
+	m->d.nodes_per_elem = npe;
+	m->d.adj = m->adj;
+	if (!with_topology)
+		return NBGPU_OK;
+	uint32_t N_edg = R.mesh_N_edges(part), N_vtx = R.mesh_N_invtx(part), N_sgm = R.mesh_N_insgm(part);
+	m->edg = malloc((2 * (size_t)N_edg + 1) * sizeof(uint32_t));
+	m->vtx = malloc(((size_t)N_vtx + 1) * sizeof(uint32_t));
+	m->sgm_sizes = malloc(((size_t)N_sgm + 1) * sizeof(uint32_t));
+	if (!m->edg || !m->vtx || !m->sgm_sizes)
+		return NBGPU_ERR_NOMEM;
+	for (uint32_t i = 0; i < N_edg; i++) {
+		m->edg[2 * i] = R.edge_1n(part, i);
+		m->edg[2 * i + 1] = R.edge_2n(part, i);
+	}
+	for (uint32_t i = 0; i < N_vtx; i++)
+		m->vtx[i] = R.invtx(part, i);
+	size_t tot = 0;
+	for (uint32_t s = 0; s < N_sgm; s++) {
+		m->sgm_sizes[s] = R.insgm_N_nodes(part, s);
+		tot += m->sgm_sizes[s];
+	}
+	m->sgm_nodes = malloc((tot + 1) * sizeof(uint32_t));
+	if (!m->sgm_nodes)
+		return NBGPU_ERR_NOMEM;
+	tot = 0;
+	for (uint32_t s = 0; s < N_sgm; s++)
+		for (uint32_t i = 0; i < m->sgm_sizes[s]; i++)
+			m->sgm_nodes[tot++] = R.insgm_node(part, s, i);
+	m->d.N_edg = N_edg;
+	m->d.edg = m->edg;
+	m->d.N_vtx = N_vtx;
+	m->d.vtx = m->vtx;
+	m->d.N_sgm = N_sgm;
+	m->d.sgm_sizes = m->sgm_sizes;
+	m->d.sgm_nodes = m->sgm_nodes;
+	return NBGPU_OK;
+}
+
+static void free_mesh(flat_mesh_t *m)
+{
+	free(m->nod); free(m->adj); free(m->edg); free(m->vtx); free(m->sgm_sizes); free(m->sgm_nodes);
+}
+
+static void read_tables(const nb_fem_elem_t *elem, nbgpu_elem_tables_t *t)
+{
+	memset(t, 0, sizeof(*t));
+	t->N_nodes = R.elem_N_nodes(elem);
+	t->N_gp = R.elem_N_gp(elem);
+	for (uint32_t g = 0; g < t->N_gp && g < 4; g++)
+		t->gp_weight[g] = R.elem_w(elem, (uint8_t)g);
+	for (uint32_t i = 0; i < t->N_nodes && i < 4; i++)
+		for (uint32_t g = 0; g < t->N_gp && g < 4; g++) {
+			t->Ni[i * t->N_gp + g] = R.elem_Ni(elem, (uint8_t)i, (uint8_t)g);
+			t->dNi_dpsi[i * t->N_gp + g] = R.elem_dpsi(elem, (uint8_t)i, (uint8_t)g);
+			t->dNi_deta[i * t->N_gp + g] = R.elem_deta(elem, (uint8_t)i, (uint8_t)g);
+		}
+}
+
+/* pipeline.h:21-30.  Values are assembled on the device into a matrix with K's
+ * pattern and written back into K's rows; F likewise. */
+int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh2D_t *const part,
+			     const nb_fem_elem_t *const elem, const nb_material_t *const material,
+			     bool enable_self_weight, double gravity[2], nb_analysis2D_t analysis2D,
+			     nb_analysis2D_params *params2D, const bool *elements_enabled)
+{
+	resolve();
+	if (M != NULL) {
+		/* the lumped mass vector belongs to the dynamic drivers, outside this hot path */
+		fprintf(stderr, "nbots_b200: pipeline_assemble_system with a mass vector is not accelerated\n");
+		return NBGPU_ERR_ARG;
+	}
+	nbgpu_elem_tables_t tab;
+	read_tables(elem, &tab);
+	flat_mesh_t fm;
+	nbgpu_matrix_t *dK = NULL;
+	nbgpu_mesh_t *dmesh = NULL;
+	double *d_F = NULL;
+	int status = 1;
+	int st = flatten_mesh(part, tab.N_nodes, 0, &fm);
+	if (st == NBGPU_OK)
+		st = nbgpu_matrix_create_from_rows(K->N, K->rows_size, K->rows_index, NULL, &dK);
+	if (st == NBGPU_OK)
+		st = nbgpu_mesh_create(fm.d.N_nod, fm.d.nod, fm.d.N_elems, fm.d.nodes_per_elem, fm.d.adj, &dmesh);
+	if (st == NBGPU_OK)
+		st = nbgpu_malloc((void **)&d_F, (size_t)K->N * sizeof(double));
+	if (st == NBGPU_OK) {
+		nbgpu_assembly_params_t ap;
+		memset(&ap, 0, sizeof(ap));
+		R.constitutive(ap.D, material, analysis2D);     /* the reference's own D (formulas.c:32-46) */
+		ap.density = R.mat_density(material);
+		for (int k = 0; k < 4; k++)
+			ap.D_void[k] = 1e-6;
+		ap.density_void = 1e-6;
+		ap.thickness = params2D->thickness;
+		ap.self_weight = enable_self_weight;
+		if (enable_self_weight) {
+			ap.gravity[0] = gravity[0];
+			ap.gravity[1] = gravity[1];
+		}
+		ap.mode = NBGPU_ASSEMBLY_GATHER;
+		st = nbgpu_assemble_elasticity2d(dK, dmesh, &tab, &ap, (const uint8_t *)elements_enabled, NULL,
+						 d_F, NULL);
+		if (st == NBGPU_OK || st == NBGPU_DISTORTED_ELEMENT) {
+			status = st;
+			st = nbgpu_matrix_get_values_rows(dK, K->rows_values);
+			if (st == NBGPU_OK)
+				st = nbgpu_copy_d2h(F, d_F, (size_t)K->N * sizeof(double));
+		}
+	}
+	nbgpu_free(d_F);
+	nbgpu_mesh_destroy(dmesh);
+	nbgpu_matrix_destroy(dK);
+	free_mesh(&fm);
+	report("pipeline_assemble_system", st);
+	return st != NBGPU_OK ? st : status;
+}
+
+/* growable ordered dof list */
+typedef struct {
+	uint32_t n, cap;
+	uint32_t *dof;
+	double *val;
+} list_t;
+
+static void push(list_t *l, uint32_t dof, double val)
+{
+	if (l->n == l->cap) {
+		l->cap = l->cap ? 2 * l->cap : 256;
+		l->dof = realloc(l->dof, l->cap * sizeof(uint32_t));
+		l->val = realloc(l->val, l->cap * sizeof(double));
+		if (!l->dof || !l->val) {
+			fprintf(stderr, "nbots_b200: out of memory\n");
+			exit(1);
+		}
+	}
+	l->dof[l->n] = dof;
+	l->val[l->n++] = val;
+}
+
+/* Walk the reference's nb_bcond_t with its own iterator and flatten it in the
+ * order nb_fem_set_bconditions applies it (set_bconditions.c:52-262). */
+static void flatten_bconditions(const nb_mesh2D_t *part, const nb_bcond_t *bcond, double factor,
+				list_t *neu, list_t *dir)
+{
+	const uint8_t N_dof = R.bc_N_dof(bcond);
+	nb_bcond_iter_t *it = malloc(R.it_memsize());
+	double val[8], val1[8], val2[8], x[2];
+	static const int order[4][2] = {{1, 1}, {1, 0}, {0, 1}, {0, 0}};   /* {NB_NEUMANN|NB_DIRICHLET, where} */
+	for (int pass = 0; pass < 4; pass++) {
+		const int kind = order[pass][0], where = order[pass][1];
+		R.it_init(it);
+		R.it_set(it, bcond, kind, where);
+		while (R.it_more(it)) {
+			R.it_next(it);
+			const uint32_t id = R.it_id(it);
+			if (kind == 1 && where == 1 && R.it_is_fn(it)) {
+				uint32_t v1 = R.insgm_node(part, id, 0);
+				x[0] = R.node_x(part, v1);
+				x[1] = R.node_y(part, v1);
+				R.it_val(it, N_dof, x, 0, val1);
+				const uint32_t n = R.insgm_N_nodes(part, id);
+				for (uint32_t i = 0; i + 1 < n; i++) {
+					const double len = R.insgm_sub_length(part, id, i);
+					const uint32_t v2 = R.insgm_node(part, id, i + 1);
+					x[0] = R.node_x(part, v2);
+					x[1] = R.node_y(part, v2);
+					R.it_val(it, N_dof, x, 0, val2);
+					for (uint8_t j = 0; j < N_dof; j++) {
+						if (!R.it_mask(it, j))
+							continue;
+						const double v = 0.5 * (val1[j] + val2[j]) * len;
+						push(neu, v1 * N_dof + j, factor * v * 0.5);
+						push(neu, v2 * N_dof + j, factor * v * 0.5);
+					}
+					v1 = v2;
+					memcpy(val1, val2, N_dof * sizeof(double));
+				}
+			} else if (kind == 1 && where == 1) {
+				const double total = R.insgm_length(part, id);
+				const uint32_t n = R.insgm_N_nodes(part, id);
+				x[0] = x[1] = 0;
+				R.it_val(it, N_dof, x, 0, val);
+				for (uint32_t i = 0; i + 1 < n; i++) {
+					const double w = R.insgm_sub_length(part, id, i) / total;
+					const double f = factor * w * 0.5;
+					for (uint32_t e = 0; e < 2; e++) {
+						const uint32_t v = R.insgm_node(part, id, i + e);
+						for (uint8_t j = 0; j < N_dof; j++)
+							if (R.it_mask(it, j))
+								push(neu, v * N_dof + j, f * val[j]);
+					}
+				}
+			} else if (kind == 1) {
+				const uint32_t v = R.invtx(part, id);
+				x[0] = x[1] = 0;
+				R.it_val(it, N_dof, x, 0, val);
+				for (uint8_t j = 0; j < N_dof; j++)
+					if (R.it_mask(it, j))
+						push(neu, v * N_dof + j, factor * val[j]);
+			} else {
+				const uint32_t n = where ? R.insgm_N_nodes(part, id) : 1;
+				for (uint32_t i = 0; i < n; i++) {
+					const uint32_t v = where ? R.insgm_node(part, id, i) : R.invtx(part, id);
+					x[0] = R.node_x(part, v);
+					x[1] = R.node_y(part, v);
+					R.it_val(it, N_dof, x, 0, val);
+					for (uint8_t j = 0; j < N_dof; j++)
+						if (R.it_mask(it, j))
+							push(dir, v * N_dof + j, factor * val[j]);
+				}
+			}
+		}
+		R.it_finish(it);
+	}
+	free(it);
+}
+
+/* static_elasticity2D.h:13-24.  Status 0 ok, 1 assembly failed, 2 solver failed
+ * (never returned by the reference either, static_elasticity2D.c:92). */
+int nb_fem_compute_2D_Solid_Mechanics(const nb_mesh2D_t *const part, const nb_fem_elem_t *const elemtype,
+				      const nb_material_t *const material, const nb_bcond_t *const bcond,
+				      bool enable_self_weight, double gravity[2], nb_analysis2D_t analysis2D,
+				      nb_analysis2D_params *params2D, const bool *elements_enabled,
+				      double *displacement, double *strain)
+{
+	resolve();
+	nbgpu_elem_tables_t tab;
+	read_tables(elemtype, &tab);
+	flat_mesh_t fm;
+	list_t neu = {0, 0, NULL, NULL}, dir = {0, 0, NULL, NULL};
+	int st = flatten_mesh(part, tab.N_nodes, 1, &fm);
+	if (st == NBGPU_OK) {
+		flatten_bconditions(part, bcond, 1.0, &neu, &dir);
+		/* the reference's own constitutive matrix (formulas.c:32-46) */
+		double D[4];
+		R.constitutive(D, material, analysis2D);
+		st = nbgpu_fem_static_elasticity2d_lists(&fm.d, &tab, D, R.mat_density(material), neu.n,
+							 neu.dof, neu.val, dir.n, dir.dof, dir.val,
+							 enable_self_weight, gravity, analysis2D,
+							 params2D->thickness, (const uint8_t *)elements_enabled,
+							 NBGPU_ASSEMBLY_GATHER, 0.0, displacement, strain, NULL);
+	}
+	free(neu.dof); free(neu.val); free(dir.dof); free(dir.val);
+	free_mesh(&fm);
+	report("nb_fem_compute_2D_Solid_Mechanics", st);
+	return st;
+}

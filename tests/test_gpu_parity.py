@@ -1,0 +1,295 @@
+"""GPU parity tests proper: every call goes through the C ABI of libnbgpu.so and is checked against
+the oracle (golden vectors from the reference + the pinned port).  Bars (BASELINE.json north_star):
+pattern bit-exact; values and displacements <= 1e-10 relative L2; CG iteration counts within +-2 %.
+Where this implementation reproduces the reference's arithmetic order (SpMV, GATHER assembly,
+boundary conditions, strain/stress) the tests demand bit-exact equality instead."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from nbots_b200 import api, capi, meshgen
+from oracle import port
+from util import FEM_CASES, bc_records, flatten_bcs, golden, mesh_of, product_bcs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_VALUES = 1e-10       # relative L2, stated by north_star
+TOL_ITERS = 0.02         # +-2 %
+
+
+def iters_close(a, b):
+    return abs(a - b) <= max(1, int(np.ceil(TOL_ITERS * b)))
+
+
+# ---------------------------------------------------------------- matrix + SpMV --
+
+@pytest.mark.parametrize("name", FEM_CASES + ["lap9_48"])
+def test_matrix_roundtrip_and_spmv_bit_exact(nbgpu_lib, name):
+    g = golden(name)
+    vals = g["K_post"] if "K_post" in g.files else g["vals"]
+    A = api.Matrix.from_csr(g["rows_size"], g["cols"], vals)
+    rs, cols = A.pattern_csr()
+    assert np.array_equal(rs, g["rows_size"]) and np.array_equal(cols, g["cols"])
+    assert np.array_equal(A.values_csr(), vals)
+    x = g["x"] if "K_post" in g.files else g["b"]
+    want = g["spmv_x"] if "K_post" in g.files else g["spmv_b"]
+    assert np.array_equal(A.spmv_host(x), want)          # same rounding as sparse.c:405-414
+    A.set_values_csr(2.0 * vals)
+    assert np.array_equal(A.values_csr(), 2.0 * vals)
+    A.reset()
+    assert not A.values_csr().any()
+
+
+def test_matrix_from_jagged_rows(nbgpu_lib):
+    """nbgpu_matrix_create_from_rows takes the reference's per-row heap blocks (struct nb_sparse_s)."""
+    g = golden("quad_cantilever_64x16")
+    rs, cols, vals = g["rows_size"], g["cols"], g["K_post"]
+    rp = port.row_ptr_of(rs)
+    rows_c = [np.ascontiguousarray(cols[rp[i]:rp[i + 1]]) for i in range(rs.size)]
+    rows_v = [np.ascontiguousarray(vals[rp[i]:rp[i + 1]]) for i in range(rs.size)]
+    pc = (C.c_void_p * rs.size)(*[a.ctypes.data for a in rows_c])
+    pv = (C.c_void_p * rs.size)(*[a.ctypes.data for a in rows_v])
+    A = api.Matrix.from_row_pointers(rs.size, rs.ctypes.data, pc, pv)
+    assert np.array_equal(A.values_csr(), vals) and np.array_equal(A.pattern_csr()[1], cols)
+    assert np.array_equal(A.spmv_host(g["x"]), g["spmv_x"])
+    out = [np.zeros_like(a) for a in rows_v]
+    po = (C.c_void_p * rs.size)(*[a.ctypes.data for a in out])
+    capi.check(nbgpu_lib.nbgpu_matrix_get_values_rows(A.h, po))
+    assert np.array_equal(np.concatenate(out), vals)
+
+
+def test_spmv_edge_cases(nbgpu_lib):
+    rng = np.random.default_rng(0)
+    # ragged rows incl. empty rows and a row as long as the matrix, N not a multiple of 32
+    for N in (1, 31, 33, 100, 257):
+        rs = rng.integers(0, min(N, 40) + 1, size=N).astype(np.uint32)
+        rs[rng.integers(0, N)] = 0
+        rs[rng.integers(0, N)] = N
+        cols = np.concatenate([np.sort(rng.choice(N, size=k, replace=False)) for k in rs]).astype(np.uint32)
+        vals = rng.standard_normal(cols.size)
+        x = rng.standard_normal(N)
+        A = api.Matrix.from_csr(rs, cols, vals)
+        assert A.stored >= A.nnz and A.n_slices == (N + 31) // 32
+        assert np.array_equal(A.spmv_host(x), port.Csr(rs, cols, vals).spmv(x))
+        assert np.array_equal(A.values_csr(), vals)
+    # signed zeros and non-finite values travel unchanged
+    rs = np.array([2, 1], dtype=np.uint32); cols = np.array([0, 1, 1], dtype=np.uint32)
+    vals = np.array([-0.0, 1.0, np.inf])
+    A = api.Matrix.from_csr(rs, cols, vals)
+    y = A.spmv_host(np.array([1.0, -0.0]))
+    want = port.Csr(rs, cols, vals).spmv(np.array([1.0, -0.0]))
+    assert np.array_equal(y, want, equal_nan=True) and np.array_equal(np.signbit(y), np.signbit(want))
+    # unsorted columns violate the nb_sparse_create invariant
+    with pytest.raises(capi.NbgpuError) as e:
+        api.Matrix.from_csr(np.array([2], dtype=np.uint32), np.array([0, 0], dtype=np.uint32), np.ones(2))
+    assert e.value.code == capi.ERR_ARG
+
+
+# ------------------------------------------------------------------------ Krylov --
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_pcg_jacobi_matches_reference(nbgpu_lib, name):
+    g = golden(name)
+    A = api.Matrix.from_csr(g["rows_size"], g["cols"], g["K_post"])
+    st, x, it, res = A.pcg_jacobi_host(g["F_post"], tol=float(g["tol"]))
+    assert st == int(g["pcg_status"])
+    assert iters_close(it, int(g["pcg_iters"])), (it, int(g["pcg_iters"]))
+    assert rel_l2(x, g["x"]) <= TOL_VALUES
+    assert res <= float(g["tol"])
+    st, x, it, res = A.cg_host(g["F_post"], tol=float(g["tol"]))
+    if int(g["cg_status"]) == 0:
+        assert st == 0 and iters_close(it, int(g["cg_iters"])) and rel_l2(x, g["x_cg"]) <= 1e-8
+    else:
+        assert st == 1 and it == int(g["cg_iters"])      # ran into max_iter = N like the reference
+
+
+def test_pcg_semantics_on_laplacian(nbgpu_lib):
+    g = golden("lap9_48")
+    A = api.Matrix.from_csr(g["rows_size"], g["cols"], g["vals"])
+    b, tol = g["b"], float(g["tol"])
+    st, x, it, res = A.pcg_jacobi_host(b, tol=tol)
+    assert st == 0 and iters_close(it, int(g["pcg_iters"])) and rel_l2(x, g["x"]) <= TOL_VALUES
+    # stale-residual rule: tolerance_reached is the residual BEFORE the last update (:84)
+    assert abs(res - float(g["pcg_res"])) <= 1e-6 * float(g["pcg_res"])
+    # max_iter exit: exactly max_iter iterations, status 1, same iterate as the reference (:86-89)
+    st, x, it, res = A.pcg_jacobi_host(b, tol=0.0, max_iter=25)
+    assert (st, it) == (1, 25) and rel_l2(x, g["x_cap"]) <= 1e-12
+    assert abs(res - float(g["cap_res"])) <= 1e-10 * float(g["cap_res"])
+    # initial guess honoured (x is in/out)
+    st, x, it, res = A.pcg_jacobi_host(b, x0=g["x0"], tol=tol)
+    assert st == 0 and iters_close(it, int(g["warm_iters"])) and rel_l2(x, g["x_warm"]) <= TOL_VALUES
+    # already converged: zero iterations, x untouched (loop never entered)
+    st, x2, it, res = A.pcg_jacobi_host(b, x0=x, tol=1e-3 * np.linalg.norm(b))
+    assert (st, it) == (0, 0) and np.array_equal(x2, x)
+    # max_iter = 0
+    st, x3, it, res = A.pcg_jacobi_host(b, tol=0.0, max_iter=0)
+    assert (st, it) == (1, 0) and not x3.any() and abs(res - np.linalg.norm(b)) <= 1e-12 * np.linalg.norm(b)
+    # plain CG
+    st, x, it, res = A.cg_host(b, tol=tol)
+    assert st == 0 and iters_close(it, int(g["cg_iters"])) and rel_l2(x, g["x_cg"]) <= TOL_VALUES
+    # deterministic reductions: two solves are bit-identical
+    r1 = A.pcg_jacobi_host(b, tol=tol)
+    r2 = A.pcg_jacobi_host(b, tol=tol)
+    assert r1[2] == r2[2] and np.array_equal(r1[1], r2[1])
+
+
+def test_pcg_device_buffers_and_chunk_boundaries(nbgpu_lib):
+    """Device-pointer entry point; iteration caps around the host's launch-chunk size."""
+    g = golden("quad_cantilever_64x16")
+    A = api.Matrix.from_csr(g["rows_size"], g["cols"], g["K_post"])
+    K = port.Csr(g["rows_size"], g["cols"], g["K_post"])
+    d_b = api.DeviceBuffer.from_host(g["F_post"])
+    for cap in (1, 31, 32, 33, 64, 65):
+        d_x = api.DeviceBuffer.zeros(A.N)
+        st, it, res = A.pcg_jacobi(d_b, d_x, max_iter=cap, tol=0.0)
+        ost, ox, oit, ores = K.pcg_jacobi(g["F_post"], max_iter=cap, tol=0.0)
+        assert (st, it) == (ost, oit) == (1, cap)
+        assert rel_l2(d_x.to_host(), ox) <= 1e-11 and abs(res - ores) <= 1e-9 * ores
+
+
+# ---------------------------------------------------------------------- assembly --
+
+def assemble_case(g, mode):
+    m = mesh_of(g)
+    K = api.Matrix.from_csr(g["rows_size"], g["cols"])
+    mesh = api.Mesh(m)
+    d_F = api.DeviceBuffer.zeros(K.N)
+    en = g["enabled"] if "enabled" in g.files else None
+    st, bad = mesh.assemble(K, d_F, float(g["E"]), float(g["nu"]), density=float(g["density"]),
+                            self_weight=bool(g["self_weight"]), gravity=tuple(g["gravity"]),
+                            analysis=int(g["analysis"]), thickness=float(g["thickness"]), enabled=en, mode=mode)
+    assert st == 0
+    return m, mesh, K, d_F
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_assembly_gather_is_bit_exact(nbgpu_lib, name):
+    g = golden(name)
+    m, mesh, K, d_F = assemble_case(g, capi.ASSEMBLY_GATHER)
+    assert np.array_equal(K.values_csr(), g["K_pre"])       # bit for bit the reference's K
+    assert np.array_equal(d_F.to_host(), g["F_pre"])
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+@pytest.mark.parametrize("mode", [capi.ASSEMBLY_ATOMIC, capi.ASSEMBLY_COLOR])
+def test_assembly_element_parallel(nbgpu_lib, name, mode):
+    g = golden(name)
+    m, mesh, K, d_F = assemble_case(g, mode)
+    assert rel_l2(K.values_csr(), g["K_pre"]) <= 1e-14
+    F = d_F.to_host()
+    assert rel_l2(F, g["F_pre"]) <= 1e-13 if g["F_pre"].any() else not F.any()
+    if mode == capi.ASSEMBLY_COLOR:                          # deterministic: same bits twice
+        m2, mesh2, K2, d_F2 = assemble_case(g, mode)
+        assert np.array_equal(K.values_csr(), K2.values_csr())
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_boundary_conditions_bit_exact(nbgpu_lib, name):
+    g = golden(name)
+    m, mesh, K, d_F = assemble_case(g, capi.ASSEMBLY_GATHER)
+    neu_dof, neu_add, dir_dof, dir_val = flatten_bcs(m, bc_records(g))
+    api.vector_add_entries(d_F, neu_dof, neu_add)
+    K.apply_dirichlet(d_F, dir_dof, dir_val)
+    assert np.array_equal(K.values_csr(), g["K_post"])
+    assert np.array_equal(d_F.to_host(), g["F_post"])
+
+
+def test_dirichlet_order_and_duplicates(nbgpu_lib):
+    """Neighbouring and repeated constrained dofs: the sequential semantics of sparse.c:416-430."""
+    g = golden("quad_cantilever_64x16")
+    rng = np.random.default_rng(5)
+    dofs = rng.choice(g["rows_size"].size, size=300, replace=True).astype(np.uint32)
+    dofs[10:20] = dofs[0:10]                                  # duplicates with different values
+    vals = rng.standard_normal(dofs.size)
+    K = api.Matrix.from_csr(g["rows_size"], g["cols"], g["K_pre"])
+    d_F = api.DeviceBuffer.from_host(g["F_pre"] + 1.0)
+    K.apply_dirichlet(d_F, dofs, vals)
+    P = port.Csr(g["rows_size"], g["cols"], g["K_pre"])
+    F = g["F_pre"] + 1.0
+    for d, v in zip(dofs, vals):
+        P.dirichlet(F, d, v)
+    assert np.array_equal(K.values_csr(), P.vals) and np.array_equal(d_F.to_host(), F)
+
+
+def test_distorted_element_is_reported(nbgpu_lib):
+    for kind in (0, 1):
+        m = meshgen.structured_mesh(6, 4, 6.0, 4.0, kind=kind)
+        npe = m.npe
+        for e in (17, 9):
+            m.adj[npe * e:npe * (e + 1)] = m.adj[npe * e:npe * (e + 1)][::-1].copy()   # clockwise
+        rs, cols = api.pattern_from_mesh(m)
+        K = api.Matrix.from_csr(rs, cols)
+        mesh = api.Mesh(m)
+        d_F = api.DeviceBuffer.zeros(K.N)
+        for mode in (capi.ASSEMBLY_GATHER, capi.ASSEMBLY_ATOMIC, capi.ASSEMBLY_COLOR):
+            st, bad = mesh.assemble(K, d_F, 1.0, 0.3, mode=mode)
+            assert st == capi.DISTORTED_ELEMENT and bad == 9     # lowest id, like the serial loop (pipeline.c:60-69)
+
+
+def test_pattern_miss_is_an_error(nbgpu_lib):
+    m = meshgen.structured_mesh(4, 4, 1.0, 1.0, kind=1)
+    rs, cols = api.pattern_from_mesh(meshgen.structured_mesh(4, 4, 1.0, 1.0, kind=0))   # no anti-diagonal
+    K = api.Matrix.from_csr(rs, cols)
+    mesh = api.Mesh(m)
+    d_F = api.DeviceBuffer.zeros(K.N)
+    with pytest.raises(capi.NbgpuError) as e:
+        mesh.assemble(K, d_F, 1.0, 0.3)
+    assert e.value.code == capi.ERR_PATTERN
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_strain_and_stress_bit_exact(nbgpu_lib, name):
+    g = golden(name)
+    m = mesh_of(g)
+    mesh = api.Mesh(m)
+    ngp = 4 if m.kind else 1
+    d_u = api.DeviceBuffer.from_host(g["x"])
+    d_e = api.DeviceBuffer.zeros(3 * ngp * m.n_elems)
+    d_s = api.DeviceBuffer.zeros(3 * ngp * m.n_elems)
+    mesh.compute_strain(d_u, d_e)
+    assert np.array_equal(d_e.to_host(), g["strain"])
+    en = g["enabled"] if "enabled" in g.files else None
+    api.stress_from_strain(m.n_elems, ngp, g["D"], d_e, d_s, enabled=en)
+    assert np.array_equal(d_s.to_host(), g["stress"])
+
+
+# ------------------------------------------------------------------------ driver --
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_fem_driver_matches_reference(nbgpu_lib, name):
+    """nbgpu_fem_static_elasticity2d == nb_fem_compute_2D_Solid_Mechanics on the same inputs."""
+    g = golden(name)
+    m = mesh_of(g)
+
+    class Desc(C.Structure):
+        _fields_ = [("N_nod", C.c_uint32), ("nod", capi.f64p), ("N_elems", C.c_uint32), ("npe", C.c_uint32),
+                    ("adj", capi.u32p), ("N_edg", C.c_uint32), ("edg", capi.u32p), ("N_vtx", C.c_uint32),
+                    ("vtx", capi.u32p), ("N_sgm", C.c_uint32), ("sgm_sizes", capi.u32p), ("sgm_nodes", capi.u32p)]
+
+    class Report(C.Structure):
+        _fields_ = [("N", C.c_uint32), ("nnz", C.c_uint64), ("iters", C.c_uint32), ("status", C.c_int32),
+                    ("residual", C.c_double), ("ms", C.c_double * 6)]
+    p = lambda a, t: a.ctypes.data_as(t)  # noqa: E731
+    d = Desc(m.n_nod, p(m.nod, capi.f64p), m.n_elems, m.npe, p(m.adj, capi.u32p), m.n_edg, p(m.edg, capi.u32p),
+             m.vtx.size, p(m.vtx, capi.u32p), m.sgm_sizes.size, p(m.sgm_sizes, capi.u32p), p(m.sgm_nodes, capi.u32p))
+    bcs, nbc = product_bcs(bc_records(g))
+    ngp = 4 if m.kind else 1
+    disp = np.zeros(2 * m.n_nod); strain = np.zeros(3 * ngp * m.n_elems)
+    grav = (C.c_double * 2)(*g["gravity"])
+    en = g["enabled"] if "enabled" in g.files else None
+    rep = Report()
+    f = nbgpu_lib.nbgpu_fem_static_elasticity2d
+    f.restype = C.c_int
+    st = f(C.byref(d), None, C.c_double(float(g["E"])), C.c_double(float(g["nu"])), C.c_double(float(g["density"])),
+           C.c_uint32(nbc), bcs, C.c_int(int(g["self_weight"])), grav, C.c_int(int(g["analysis"])),
+           C.c_double(float(g["thickness"])), None if en is None else en.ctypes.data_as(capi.u8p),
+           C.c_int(capi.ASSEMBLY_GATHER), C.c_double(float(g["tol"])), p(disp, capi.f64p), p(strain, capi.f64p),
+           C.byref(rep))
+    assert st == 0, nbgpu_lib.nbgpu_last_error()
+    assert (rep.N, rep.nnz) == (g["rows_size"].size, g["cols"].size)
+    assert iters_close(rep.iters, int(g["pcg_iters"])) and rep.status == int(g["pcg_status"])
+    assert rel_l2(disp, g["x"]) <= TOL_VALUES
+    assert rel_l2(strain, g["strain"]) <= 1e-9
+    if name == "beam_cantilever_trg1000":      # the reference's own assert (utest static_elasticity2D.c:118)
+        assert abs(np.sqrt((disp.reshape(-1, 2) ** 2).sum(axis=1)).max() - 1.00701e-1) < 1e-6

@@ -1,0 +1,105 @@
+"""CPU: the product's host-side logic and the C-ABI surface (no compute calls: there is no GPU here
+and the library has no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nbots_b200 import api, capi, meshgen
+from oracle import port
+from util import FEM_CASES, bc_records, flatten_bcs, golden, mesh_of
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    text = open(capi.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(nbgpu_[a-z0-9_]+)\s*\(", text)))
+    assert len(declared) > 40
+    missing = [n for n in declared if not hasattr(L, n)]
+    assert not missing, f"declared in include/nbgpu.h but not exported: {missing}"
+    bound = set(capi.SIGNATURES) | {"nbgpu_bcond_flatten", "nbgpu_fem_static_elasticity2d",
+                                    "nbgpu_fem_static_elasticity2d_lists"}
+    assert not [n for n in declared if n not in bound and not n.startswith("nbgpu_comm")], \
+        "every declared entry point needs a ctypes signature"
+
+
+def test_shim_exports_reference_names():
+    S = C.CDLL(capi.SHIM_PATH)
+    for name in ("nb_sparse_solve_CG_precond_Jacobi", "nb_sparse_solve_conjugate_gradient",
+                 "nb_sparse_multiply_vector", "pipeline_assemble_system", "nb_fem_compute_2D_Solid_Mechanics"):
+        assert hasattr(S, name)
+
+
+def test_compute_fails_loudly_without_a_device():
+    L = capi.lib()
+    if L.nbgpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    rs, cols, vals = meshgen.laplacian9_csr(4)
+    with pytest.raises(capi.NbgpuError) as e:
+        api.Matrix.from_csr(rs, cols, vals)
+    assert e.value.code == capi.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+@pytest.mark.parametrize("use_edges", [True, False])
+def test_pattern_builder_is_bit_exact(name, use_edges):
+    g = golden(name)
+    rs, cols = api.pattern_from_mesh(mesh_of(g), 2, use_edges=use_edges)
+    assert np.array_equal(rs, g["rows_size"]) and np.array_equal(cols, g["cols"])
+
+
+def test_pattern_builder_scalar_and_ragged():
+    g = golden("lap9_48")
+    # vars_per_node = 1 on a quad grid gives the 9-point pattern of config 3
+    m = meshgen.structured_mesh(47, 47, 1.0, 1.0, kind=1)
+    rs, cols = api.pattern_from_mesh(m, 1)
+    assert np.array_equal(rs, g["rows_size"]) and np.array_equal(cols, g["cols"])
+    # isolated node (no element touches it): a row holding only its diagonal, like nb_sparse_create
+    m = meshgen.structured_mesh(2, 1, 2.0, 1.0, kind=0)
+    m.nod = np.concatenate([m.nod, [9.0, 9.0]])
+    rs, cols = api.pattern_from_mesh(m, 2)
+    prs, pcols = port.pattern_from_mesh(m, 2)
+    assert np.array_equal(rs, prs) and np.array_equal(cols, pcols) and rs[-1] == 2
+
+
+def test_tables_and_constitutive_match_reference():
+    for npe, et in ((3, 0), (4, 1)):
+        t = api.elem_tables(npe)
+        n, g, w, Ni, dp, de = port.elem_tables(et)
+        assert (t.N_nodes, t.N_gp) == (n, g)
+        assert np.array_equal(np.array(t.gp_weight[:g]), w) and np.array_equal(np.array(t.Ni[:n * g]), Ni)
+        assert np.array_equal(np.array(t.dNi_dpsi[:n * g]), dp) and np.array_equal(np.array(t.dNi_deta[:n * g]), de)
+    for name in FEM_CASES:
+        g = golden(name)
+        # includes analysis = 1 ("plane strain"): the reference still yields the plane-stress D
+        assert np.array_equal(api.constitutive_matrix(float(g["E"]), float(g["nu"]), int(g["analysis"])), g["D"])
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_bcond_flatten_reproduces_reference_bcs(name):
+    """The flattened (ordered) dof lists, applied sequentially with the ORACLE's Dirichlet elimination,
+    must give the reference's post-BC system bit for bit."""
+    g = golden(name)
+    m = mesh_of(g)
+    neu_dof, neu_add, dir_dof, dir_val = flatten_bcs(m, bc_records(g))
+    K = port.Csr(g["rows_size"], g["cols"], g["K_pre"])
+    F = g["F_pre"].copy()
+    for d, a in zip(neu_dof, neu_add):
+        F[d] += a
+    for d, v in zip(dir_dof, dir_val):
+        K.dirichlet(F, d, v)
+    assert np.array_equal(F, g["F_post"]) and np.array_equal(K.vals, g["K_post"])
+
+
+def test_meshgen_counts():
+    for nx, ny in ((64, 16), (7, 3)):
+        m = meshgen.structured_mesh(nx, ny, 1.0, 1.0)
+        rs, cols = api.pattern_from_mesh(m, 2)
+        assert (rs.size, cols.size) == meshgen.quad_counts(nx, ny)
+    assert meshgen.quad_counts(1000, 500) == (1003002, 18018004)
+    assert meshgen.quad_counts(4000, 2000) == (16012002, 288072004)    # Q16
+    a = meshgen.uniform_rhs(100, seed=5)
+    assert np.array_equal(a[10:30], meshgen.uniform_rhs(20, seed=5, start=10))
