@@ -131,6 +131,17 @@ int nbgpu_cg_host(const nbgpu_matrix_t *A, const double *b, double *x,
 		  uint32_t max_iter, double tolerance,
 		  uint32_t *niter_performed, double *tolerance_reached);
 
+/* Order of the solvers' dot-product reductions.
+ *   0 (default)  deterministic parallel tree, fused into the kernels;
+ *   1            verification mode: one thread sums in index order, exactly as
+ *                the reference's single-threaded loops do (the FEM driver runs
+ *                the solver with omp_parallel_threads = 1,
+ *                static_elasticity2D.c:90).  All other arithmetic of the solver
+ *                already rounds like the reference, so a solve in this mode is
+ *                bit-identical to the reference's: same iterates, same iteration
+ *                count, same tolerance_reached.  Slow; for parity checks. */
+int nbgpu_set_reduction_order(int mode);
+
 /* Per-kernel timing of the solvers: when enabled, CUDA events bracket the three
  * kernels of each of the first 256 iterations of the next solves, on the
  * library's stream.  _get returns the summed durations [SpMV+dot, update,

@@ -80,6 +80,7 @@ SIGNATURES = {
     "nbgpu_cg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, u32p, f64p]),
     "nbgpu_pcg_jacobi_host": (C.c_int, [C.c_void_p, f64p, f64p, C.c_uint32, C.c_double, u32p, f64p]),
     "nbgpu_cg_host": (C.c_int, [C.c_void_p, f64p, f64p, C.c_uint32, C.c_double, u32p, f64p]),
+    "nbgpu_set_reduction_order": (C.c_int, [C.c_int]),
     "nbgpu_krylov_profile": (C.c_int, [C.c_int]),
     "nbgpu_krylov_profile_get": (C.c_int, [f64p, u32p]),
     "nbgpu_pattern_from_mesh": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, u32p, C.c_uint32, u32p, C.c_uint32,

@@ -31,7 +31,7 @@
 #include <cstring>
 #include <vector>
 
-#include "spmv.cuh"
+#include "sell_stream.cuh"
 
 using namespace nbgpu;
 
@@ -88,6 +88,8 @@ krylov_init_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ s
 			}
 		}
 	}
+	if (!partials)
+		return;
 	double tot[2];
 	if (grid_reduce<2>(dots, partials, &st->ticket, tot) && threadIdx.x == 0) {
 		st->gg[0] = tot[0];
@@ -131,12 +133,84 @@ krylov_spmv_kernel(uint32_t k, uint32_t N, uint32_t n_slices, const uint32_t *__
 			dots[0] = __dadd_rn(dots[0], __dmul_rn(__ldg(p + row), acc));
 		}
 	}
+	if (!partials)
+		return;
+	double tot[1];
+	if (grid_reduce<1>(dots, partials, &st->ticket, tot) && threadIdx.x == 0)
+		st->pw = tot[0];
+}
+
+// ---- the same two kernels with the matrix streamed through shared memory (sell_stream.cuh) ----
+template <bool JACOBI, bool BLOCKED>
+__global__ void __launch_bounds__(kBlock, 2)
+krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ b,
+			  const double *__restrict__ x, double *__restrict__ g, double *__restrict__ p,
+			  double *__restrict__ q, double *__restrict__ diag, double *partials, KrylovState *st)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	double dots[2] = {0.0, 0.0};
+	sell_stream_rows<BLOCKED, JACOBI>(A, x, cfg, smem, [&](uint32_t row, double acc, double d) {
+		if (row < A.N) {
+			const double gi = __dsub_rn(acc, b[row]);
+			g[row] = gi;
+			dots[0] = __dadd_rn(dots[0], __dmul_rn(gi, gi));
+			if (JACOBI) {
+				const double qi = __ddiv_rn(gi, d);
+				diag[row] = d;
+				q[row] = qi;
+				p[row] = -qi;
+				dots[1] = __dadd_rn(dots[1], __dmul_rn(gi, qi));
+			} else {
+				p[row] = -gi;
+			}
+		}
+	});
+	if (!partials)
+		return;
+	double tot[2];
+	if (grid_reduce<2>(dots, partials, &st->ticket, tot) && threadIdx.x == 0) {
+		st->gg[0] = tot[0];
+		st->gq[0] = JACOBI ? tot[1] : tot[0];
+	}
+}
+
+template <bool BLOCKED>
+__global__ void __launch_bounds__(kBlock, 2)
+krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, const double *__restrict__ p,
+			  double *__restrict__ w, double *partials, KrylovState *st)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	if (*(volatile int32_t *)&st->done)
+		return;
+	{
+		const double gg = st->gg[gate_slot(k)];
+		const bool active = gg > st->tol2 && k < st->max_iter;
+		if (!active) {
+			if (blockIdx.x == 0 && threadIdx.x == 0) {
+				st->k_final = k;
+				st->gg_final = gg;
+				__threadfence();
+				st->done = 1;
+			}
+			return;
+		}
+	}
+	double dots[1] = {0.0};
+	sell_stream_rows<BLOCKED, false>(A, p, cfg, smem, [&](uint32_t row, double acc, double) {
+		if (row < A.N) {
+			w[row] = acc;
+			dots[0] = __dadd_rn(dots[0], __dmul_rn(__ldg(p + row), acc));
+		}
+	});
+	if (!partials)
+		return;
 	double tot[1];
 	if (grid_reduce<1>(dots, partials, &st->ticket, tot) && threadIdx.x == 0)
 		st->pw = tot[0];
 }
 
 // K2: x += a p, g += a w, q = g / diag, gq' = g.q, gg' = g.g   (:59-68)
+// Two elements per thread and trip: all ten loads are issued before the first use.
 template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock)
 krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const double *__restrict__ w,
@@ -148,18 +222,40 @@ krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const
 	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);
 	double dots[2] = {0.0, 0.0};
 	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-		const double pi = p[i], wi = w[i];
-		x[i] = __dadd_rn(x[i], __dmul_rn(alpha, pi));
-		const double gi = __dadd_rn(g[i], __dmul_rn(alpha, wi));
-		g[i] = gi;
-		dots[0] = __dadd_rn(dots[0], __dmul_rn(gi, gi));
+	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < N; i0 += 2 * stride) {
+		const uint32_t i1 = i0 + stride;
+		const bool has1 = i1 < N;
+		const uint32_t j1 = has1 ? i1 : i0;
+		const double p0 = p[i0], w0 = w[i0], x0 = x[i0], g0 = g[i0];
+		const double p1 = p[j1], w1 = w[j1], x1 = x[j1], g1 = g[j1];
+		double d0 = 1.0, d1 = 1.0;
 		if (JACOBI) {
-			const double qi = __ddiv_rn(gi, diag[i]);
-			q[i] = qi;
-			dots[1] = __dadd_rn(dots[1], __dmul_rn(gi, qi));
+			d0 = diag[i0];
+			d1 = diag[j1];
+		}
+		const double gn0 = __dadd_rn(g0, __dmul_rn(alpha, w0));
+		const double gn1 = __dadd_rn(g1, __dmul_rn(alpha, w1));
+		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
+		g[i0] = gn0;
+		dots[0] = __dadd_rn(dots[0], __dmul_rn(gn0, gn0));
+		if (JACOBI) {
+			const double q0 = __ddiv_rn(gn0, d0);
+			q[i0] = q0;
+			dots[1] = __dadd_rn(dots[1], __dmul_rn(gn0, q0));
+		}
+		if (has1) {
+			x[i1] = __dadd_rn(x1, __dmul_rn(alpha, p1));
+			g[i1] = gn1;
+			dots[0] = __dadd_rn(dots[0], __dmul_rn(gn1, gn1));
+			if (JACOBI) {
+				const double q1 = __ddiv_rn(gn1, d1);
+				q[i1] = q1;
+				dots[1] = __dadd_rn(dots[1], __dmul_rn(gn1, q1));
+			}
 		}
 	}
+	if (!partials)
+		return;   // reference-order reductions are done by seq_dot_kernel
 	double tot[2];
 	if (grid_reduce<2>(dots, partials, &st->ticket, tot) && threadIdx.x == 0) {
 		st->gg[(k + 1) % 3u] = tot[0];
@@ -176,16 +272,66 @@ krylov_dir_kernel(uint32_t k, uint32_t N, const double *__restrict__ q, double *
 		return;
 	const double beta = __ddiv_rn(st->gq[(k + 1) & 1], st->gq[k & 1]);
 	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
-		p[i] = __dadd_rn(-q[i], __dmul_rn(beta, p[i]));
+	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < N; i0 += 2 * stride) {
+		const uint32_t i1 = i0 + stride;
+		const bool has1 = i1 < N;
+		const uint32_t j1 = has1 ? i1 : i0;
+		const double q0 = q[i0], p0 = p[i0], q1 = q[j1], p1 = p[j1];
+		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, p0));
+		if (has1)
+			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
+	}
 }
 
-int vector_grid(uint32_t N)
+// Verification mode (nbgpu_set_reduction_order(1)): the dot products are summed
+// by ONE thread in index order, exactly like the reference's single-threaded
+// loops (the FEM driver passes omp_parallel_threads = 1,
+// static_elasticity2D.c:90).  Every other operation of the solver already
+// rounds like the reference, so in this mode the whole solve -- iterates,
+// iteration count, tolerance_reached -- is bit-identical to the reference's.
+// A warp loads 32 products at a time; lane 0 adds them in order.
+__global__ void seq_dot_kernel(uint32_t N, const double *__restrict__ a1, const double *__restrict__ b1,
+			       double *out1, const double *__restrict__ a2, const double *__restrict__ b2,
+			       double *out2, const KrylovState *st)
 {
-	int64_t want = ((int64_t)N + kBlock - 1) / kBlock;
-	int64_t cap = std::min<int64_t>((int64_t)ctx().sm_count * 8, kMaxPartialBlocks);
-	return (int)std::max<int64_t>(1, std::min(want, cap));
+	if (*(volatile const int32_t *)&st->done)
+		return;
+	const uint32_t lane = threadIdx.x;
+	double s1 = 0.0, s2 = 0.0;
+	for (uint32_t base = 0; base < N; base += 32) {
+		const uint32_t i = base + lane;
+		const double t1 = i < N ? __dmul_rn(a1[i], b1[i]) : 0.0;
+		const double t2 = (a2 && i < N) ? __dmul_rn(a2[i], b2[i]) : 0.0;
+		const uint32_t n = min(32u, N - base);
+		for (uint32_t l = 0; l < n; l++) {
+			const double u1 = __shfl_sync(0xffffffffu, t1, l);
+			const double u2 = __shfl_sync(0xffffffffu, t2, l);
+			s1 = __dadd_rn(s1, u1);
+			s2 = __dadd_rn(s2, u2);
+		}
+	}
+	if (lane == 0) {
+		*out1 = s1;
+		if (out2)
+			*out2 = a2 ? s2 : s1;
+	}
 }
+
+// Persistent grid of one kernel: exactly the number of CTAs that are resident at
+// once (SMs x occupancy), so the grid-stride loops run as a single full wave.
+template <typename Kernel>
+int resident_grid(Kernel kernel, int64_t want_blocks)
+{
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm < 1) {
+		cudaGetLastError();
+		per_sm = 1;
+	}
+	int64_t cap = std::min<int64_t>((int64_t)ctx().sm_count * per_sm, kMaxPartialBlocks);
+	return (int)std::max<int64_t>(1, std::min(want_blocks, cap));
+}
+
+bool g_seq_dots = false;
 
 cudaEvent_t g_poll_ev[2] = {nullptr, nullptr};
 
@@ -232,16 +378,52 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 	hst[2].max_iter = max_iter;
 	NB_CUDA(cudaMemcpyAsync(st, &hst[2], sizeof(KrylovState), cudaMemcpyHostToDevice, c.stream));
 
-	const int sgrid = spmv_grid(A->n_slices), vgrid = vector_grid(N);
-	if (jacobi)
-		krylov_init_kernel<true><<<sgrid, kBlock, 0, c.stream>>>(
+	const int64_t slice_blocks = ((int64_t)A->n_slices * 32 + kBlock - 1) / kBlock;
+	const int64_t vec_blocks = ((int64_t)N + 2 * kBlock - 1) / (2 * kBlock);
+	const int igrid = jacobi ? resident_grid(krylov_init_kernel<true>, slice_blocks)
+				 : resident_grid(krylov_init_kernel<false>, slice_blocks);
+	const int sgrid = resident_grid(krylov_spmv_kernel, slice_blocks);
+	// streamed (TMA) path: same kernels, matrix staged through shared memory
+	const SellView V{N, A->n_slices, A->d_slice_off, A->d_val, A->blocked ? A->d_bcol : A->d_col};
+	StreamConfig scfg, icfg;
+	const void *sk = A->blocked ? (const void *)krylov_spmv_stream_kernel<true>
+				    : (const void *)krylov_spmv_stream_kernel<false>;
+	const void *ik = jacobi ? (A->blocked ? (const void *)krylov_init_stream_kernel<true, true>
+					      : (const void *)krylov_init_stream_kernel<true, false>)
+				: (A->blocked ? (const void *)krylov_init_stream_kernel<false, true>
+					      : (const void *)krylov_init_stream_kernel<false, false>);
+	const bool stream = stream_config(A, sk, &scfg) && stream_config(A, ik, &icfg);
+	const int ugrid = jacobi ? resident_grid(krylov_update_kernel<true>, vec_blocks)
+				 : resident_grid(krylov_update_kernel<false>, vec_blocks);
+	const int dgrid = resident_grid(krylov_dir_kernel, vec_blocks);
+	const bool seq = g_seq_dots;
+	double *partials = seq ? nullptr : c.partials;
+	if (stream) {
+		if (jacobi && A->blocked)
+			krylov_init_stream_kernel<true, true><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
+				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
+		else if (jacobi)
+			krylov_init_stream_kernel<true, false><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
+				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
+		else if (A->blocked)
+			krylov_init_stream_kernel<false, true><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
+				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
+		else
+			krylov_init_stream_kernel<false, false><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
+				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
+	} else if (jacobi)
+		krylov_init_kernel<true><<<igrid, kBlock, 0, c.stream>>>(
 			N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, d_b, d_x, g, p, q, diag,
-			c.partials, st);
+			partials, st);
 	else
-		krylov_init_kernel<false><<<sgrid, kBlock, 0, c.stream>>>(
+		krylov_init_kernel<false><<<igrid, kBlock, 0, c.stream>>>(
 			N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, d_b, d_x, g, p, q, diag,
-			c.partials, st);
+			partials, st);
 	NB_LAUNCHED();
+	if (seq) {
+		seq_dot_kernel<<<1, 32, 0, c.stream>>>(N, g, g, &st->gg[0], jacobi ? g : nullptr, q, &st->gq[0], st);
+		NB_LAUNCHED();
+	}
 
 	g_prof_recorded = 0;
 	if (g_prof_on && g_prof_ev.empty()) {
@@ -259,21 +441,37 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 			const bool prof = g_prof_on && k < kProfIters;
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k], c.stream));
-			krylov_spmv_kernel<<<sgrid, kBlock, 0, c.stream>>>(
-				k, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, p, w, c.partials, st);
+			if (stream && A->blocked)
+				krylov_spmv_stream_kernel<true><<<scfg.grid, kBlock, scfg.smem_bytes, c.stream>>>(
+					k, V, scfg, p, w, partials, st);
+			else if (stream)
+				krylov_spmv_stream_kernel<false><<<scfg.grid, kBlock, scfg.smem_bytes, c.stream>>>(
+					k, V, scfg, p, w, partials, st);
+			else
+				krylov_spmv_kernel<<<sgrid, kBlock, 0, c.stream>>>(
+					k, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, p, w, partials, st);
 			NB_LAUNCHED();
+			if (seq) {
+				seq_dot_kernel<<<1, 32, 0, c.stream>>>(N, p, w, &st->pw, nullptr, nullptr, nullptr, st);
+				NB_LAUNCHED();
+			}
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 1], c.stream));
 			if (jacobi)
-				krylov_update_kernel<true><<<vgrid, kBlock, 0, c.stream>>>(
-					k, N, p, w, diag, d_x, g, q, c.partials, st);
+				krylov_update_kernel<true><<<ugrid, kBlock, 0, c.stream>>>(
+					k, N, p, w, diag, d_x, g, q, partials, st);
 			else
-				krylov_update_kernel<false><<<vgrid, kBlock, 0, c.stream>>>(
-					k, N, p, w, diag, d_x, g, q, c.partials, st);
+				krylov_update_kernel<false><<<ugrid, kBlock, 0, c.stream>>>(
+					k, N, p, w, diag, d_x, g, q, partials, st);
 			NB_LAUNCHED();
+			if (seq) {
+				seq_dot_kernel<<<1, 32, 0, c.stream>>>(N, g, g, &st->gg[(k + 1) % 3u], jacobi ? g : nullptr,
+								       q, &st->gq[(k + 1) & 1], st);
+				NB_LAUNCHED();
+			}
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 2], c.stream));
-			krylov_dir_kernel<<<vgrid, kBlock, 0, c.stream>>>(k, N, q, p, st);
+			krylov_dir_kernel<<<dgrid, kBlock, 0, c.stream>>>(k, N, q, p, st);
 			NB_LAUNCHED();
 			if (prof) {
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 3], c.stream));
@@ -358,6 +556,13 @@ int solve_host(const nbgpu_matrix_t *A, const double *b, double *x, uint32_t max
 }  // namespace
 
 extern "C" {
+
+int nbgpu_set_reduction_order(int mode)
+{
+	NB_ARG(mode == 0 || mode == 1);
+	g_seq_dots = mode == 1;
+	return NBGPU_OK;
+}
 
 int nbgpu_krylov_profile(int enable)
 {

@@ -55,6 +55,49 @@ csr_to_sell_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ r
 	}
 }
 
+// Does the pattern have the 2-dofs-per-node block structure?  Lanes 2k, 2k+1 of a
+// slice hold rows 2i, 2i+1; *not_blocked is raised on the first violation.
+__global__ void __launch_bounds__(kBlock)
+check_blocked_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
+		     const uint32_t *__restrict__ sell_col, int *not_blocked)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
+		const uint32_t off = slice_off[s], width = slice_off[s + 1] - off;
+		bool bad = (width & 1u) != 0;
+		for (uint32_t j = 0; j + 1 < width; j += 2) {
+			const uint32_t c0 = sell_col[((size_t)off + j) * kSliceRows + lane];
+			const uint32_t c1 = sell_col[((size_t)off + j + 1) * kSliceRows + lane];
+			const uint32_t p0 = __shfl_xor_sync(0xffffffffu, c0, 1);
+			if (c0 == kPadCol)
+				bad |= c1 != kPadCol;
+			else
+				bad |= (c0 & 1u) != 0 || c1 != c0 + 1;
+			bad |= p0 != c0;
+		}
+		if (bad)
+			*not_blocked = 1;
+	}
+	(void)N;
+}
+
+__global__ void __launch_bounds__(kBlock)
+build_bcol_kernel(uint32_t n_slices, const uint32_t *__restrict__ slice_off,
+		  const uint32_t *__restrict__ sell_col, uint32_t *__restrict__ bcol)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
+		const uint32_t off = slice_off[s], width = slice_off[s + 1] - off;
+		// 16 node pairs x width/2 blocks; lane handles node pair (lane & 15), blocks lane>>4, +2, ...
+		for (uint32_t jb = lane >> 4; jb < (width >> 1); jb += 2) {
+			const uint32_t c = sell_col[((size_t)off + 2 * jb) * kSliceRows + 2 * (lane & 15)];
+			bcol[((size_t)(off >> 1) + jb) * 16u + (lane & 15)] = (c == kPadCol) ? kPadCol : (c >> 1);
+		}
+	}
+}
+
 __global__ void __launch_bounds__(kBlock)
 sell_to_csr_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
 		   const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ sell_col,
@@ -262,6 +305,22 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 		set_error("row columns must be strictly ascending and < N (nb_sparse_create invariant)");
 		return NBGPU_ERR_ARG;
 	}
+	if (d_cols && A->n_slices && (A->N & 1u) == 0 && !getenv("NBGPU_NO_BLOCKED")) {
+		// pattern (re)built: look for the 2-dofs-per-node block structure
+		NB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), c.stream));
+		check_blocked_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
+			A->N, A->n_slices, A->d_slice_off, A->d_col, (int *)bad.p);
+		NB_LAUNCHED();
+		NB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+		NB_CUDA(cudaStreamSynchronize(c.stream));
+		if (!h_bad) {
+			NB_CUDA(cudaMalloc(&A->d_bcol, std::max<size_t>(1, A->stored / 4) * sizeof(uint32_t)));
+			build_bcol_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
+				A->n_slices, A->d_slice_off, A->d_col, A->d_bcol);
+			NB_LAUNCHED();
+			A->blocked = true;
+		}
+	}
 	return NBGPU_OK;
 }
 
@@ -296,6 +355,7 @@ int nbgpu_matrix_destroy(nbgpu_matrix_t *A)
 		cudaFree(A->d_slice_off);
 		cudaFree(A->d_val);
 		cudaFree(A->d_col);
+		cudaFree(A->d_bcol);
 	}
 	delete A;
 	return NBGPU_OK;

@@ -23,6 +23,11 @@ struct nbgpu_matrix_s {
 	uint32_t *d_slice_off = nullptr;      // [n_slices + 1]
 	double *d_val = nullptr;              // [stored]
 	uint32_t *d_col = nullptr;            // [stored]
+	// 2x2-block structure (2 dofs per node): rows 2i, 2i+1 share their columns and
+	// columns come in (2c, 2c+1) pairs.  Then d_bcol holds one node id per block:
+	// block jb of the node pair nl of slice s sits at (slice_off[s]/2 + jb) * 16 + nl.
+	bool blocked = false;
+	uint32_t *d_bcol = nullptr;           // [stored / 4]
 	std::vector<uint32_t> h_rows_size;    // host copy of the pattern's row lengths
 	std::vector<uint64_t> h_row_ptr;      // CSR offsets (host), for value import/export
 };

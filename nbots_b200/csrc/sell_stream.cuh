@@ -1,0 +1,244 @@
+// sell_stream.cuh -- the matrix stream of the SELL-32 kernels, staged through
+// shared memory with bulk asynchronous copies (TMA, `cp.async.bulk`, SASS
+// UBLKCP) and mbarriers.
+//
+// Why: SpMV here is a pure HBM stream (12 B per stored entry, used once) plus a
+// cached gather.  With plain loads the bytes in flight per SM are bounded by
+// registers x resident warps, and the dependent gather sits between two batches
+// of streaming loads, so the DRAM pipe idles (ncu, round 1: 48 % DRAM
+// utilisation at 40 % achieved occupancy).  Here every warp owns a small ring
+// of shared-memory stages; one lane issues the bulk copies of the warp's NEXT
+// slices (values and column ids are each one contiguous block per slice) while
+// all 32 lanes consume the current one.  The bytes in flight are
+// stages x slice size x warps -- independent of registers and occupancy -- and
+// the consumers touch global memory only for the gather of x.
+//
+// A warp is fully self-contained (its own stages, its own mbarriers, producer =
+// its lane 0): no block-level synchronisation anywhere in the stream.
+//
+// BLOCKED layout: the elasticity matrix has 2 dofs per node, so rows 2i, 2i+1
+// share their column pattern and columns come in (2c, 2c+1) pairs.  When the
+// pattern has that structure (checked at creation) the column stream stores one
+// NODE id per 2x2 block (a quarter of the ids: 9 instead of 12 bytes per entry)
+// and the gather fetches x[2c], x[2c+1] as one 16-byte load.  The accumulation
+// order per row is unchanged.
+#pragma once
+
+#include "spmv.cuh"
+
+namespace nbgpu {
+
+// ------------------------------------------------------------------ PTX ----
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+		     : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile("{\n"
+			     ".reg .pred p;\n"
+			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+			     "selp.u32 %0, 1, 0, p;\n"
+			     "}\n"
+			     : "=r"(done)
+			     : "r"(smem_addr(bar)), "r"(parity)
+			     : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+	uint64_t policy;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+	return policy;
+}
+// global -> shared bulk copy (bytes and both addresses multiples of 16), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+					 uint64_t policy)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+		     "[%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(dst)),
+		     "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+		     : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ double2 ld_gather_f64x2(const double *p)
+{
+	double2 r;
+	asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+	return r;
+}
+
+// ------------------------------------------------------------- geometry ----
+constexpr int kStreamWarps = kBlock / 32;      // consumer warps per CTA
+constexpr int kStreamMaxStages = 6;
+constexpr int kGatherBatch = 9;                // gathers in flight per lane
+
+struct StreamConfig {
+	uint32_t cap;          // stage capacity in columns (>= widest slice)
+	uint32_t stages;       // ring depth per warp
+	uint32_t stage_bytes;  // cap * (256 + 128) or cap * (256 + 32) when blocked
+	uint32_t smem_bytes;   // dynamic shared memory per CTA
+	int grid;              // resident CTAs
+};
+
+__host__ __device__ inline uint32_t stream_stage_bytes(uint32_t cap, bool blocked)
+{
+	return cap * (kSliceRows * 8u) + (blocked ? cap * 32u : cap * (kSliceRows * 4u));
+}
+
+struct SellView {
+	uint32_t N, n_slices;
+	const uint32_t *slice_off;
+	const double *val;
+	const uint32_t *col;    // per-entry column ids, or per-block node ids when BLOCKED
+};
+
+// Runs `body(row, acc, diag)` for every row of the slices this warp owns
+// (slices warp, warp + total_warps, ...), acc = sum_j A[row][j] x[col_j] in
+// ascending column order with separately rounded products and sums.
+template <bool BLOCKED, bool WANT_DIAG, typename Body>
+__device__ __forceinline__ void sell_stream_rows(const SellView A, const double *__restrict__ x,
+						 const StreamConfig cfg, unsigned char *smem, Body body)
+{
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t total_warps = gridDim.x * kStreamWarps;
+	const uint32_t first = blockIdx.x * kStreamWarps + warp;
+	// shared memory: [warps][stages][stage_bytes] | [warps][stages] mbarriers | [warps][stages] {off,width}
+	unsigned char *ring = smem + (size_t)warp * cfg.stages * cfg.stage_bytes;
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kStreamWarps * cfg.stages * cfg.stage_bytes) +
+			 warp * kStreamMaxStages;
+	uint2 *meta = reinterpret_cast<uint2 *>(smem + (size_t)kStreamWarps * cfg.stages * cfg.stage_bytes +
+						 kStreamWarps * kStreamMaxStages * sizeof(uint64_t)) +
+		      warp * kStreamMaxStages;
+	const uint32_t val_bytes_per_col = kSliceRows * 8u;
+	const uint32_t col_bytes_per_col = BLOCKED ? 32u : kSliceRows * 4u;
+
+	uint64_t policy = 0;
+	if (lane == 0) {
+		for (uint32_t s = 0; s < cfg.stages; s++)
+			mbar_init(bars + s, 1);
+		fence_mbar_init();
+		fence_proxy_async();
+		policy = l2_evict_first_policy();
+	}
+	__syncwarp();
+
+	// producer (lane 0): fill stage `st` with slice `s`
+	auto issue = [&](uint32_t st, uint32_t s) {
+		const uint32_t off = __ldg(A.slice_off + s), width = __ldg(A.slice_off + s + 1) - off;
+		meta[st] = make_uint2(off, width);
+		unsigned char *dst = ring + (size_t)st * cfg.stage_bytes;
+		const uint32_t vb = width * val_bytes_per_col, cb = width * col_bytes_per_col;
+		mbar_arrive_expect_tx(bars + st, vb + cb);
+		if (width) {
+			bulk_g2s(dst, A.val + (size_t)off * kSliceRows, vb, bars + st, policy);
+			const unsigned char *csrc = reinterpret_cast<const unsigned char *>(A.col) +
+						    (size_t)off * col_bytes_per_col;
+			bulk_g2s(dst + (size_t)cfg.cap * val_bytes_per_col, csrc, cb, bars + st, policy);
+		}
+	};
+	if (lane == 0)
+		for (uint32_t st = 0; st < cfg.stages; st++) {
+			const uint64_t s = (uint64_t)first + (uint64_t)st * total_warps;
+			if (s < A.n_slices)
+				issue(st, (uint32_t)s);
+		}
+	__syncwarp();
+
+	uint32_t n = 0;
+	for (uint64_t s64 = first; s64 < A.n_slices; s64 += total_warps, n++) {
+		const uint32_t s = (uint32_t)s64;
+		const uint32_t st = n % cfg.stages, parity = (n / cfg.stages) & 1u;
+		mbar_wait(bars + st, parity);
+		const uint2 m = meta[st];
+		const uint32_t width = m.y;
+		const unsigned char *stage = ring + (size_t)st * cfg.stage_bytes;
+		const double *sval = reinterpret_cast<const double *>(stage) + lane;
+		const uint32_t row = s * kSliceRows + lane;
+		const uint32_t safe = min(row, A.N - 1);
+		double acc = 0.0, diag = 0.0;
+		if (!BLOCKED) {
+			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + lane;
+			for (uint32_t j0 = 0; j0 < width; j0 += kGatherBatch) {
+				uint32_t cj[kGatherBatch];
+				double xj[kGatherBatch];
+#pragma unroll
+				for (int u = 0; u < kGatherBatch; u++)
+					cj[u] = (j0 + u < width) ? scol[(j0 + u) * kSliceRows] : kPadCol;
+#pragma unroll
+				for (int u = 0; u < kGatherBatch; u++)
+					xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? safe : cj[u]));
+#pragma unroll
+				for (int u = 0; u < kGatherBatch; u++) {
+					const double v = (j0 + u < width) ? sval[(j0 + u) * kSliceRows] : 0.0;
+					const double t = __dmul_rn(v, xj[u]);
+					acc = (cj[u] == kPadCol) ? acc : __dadd_rn(acc, t);
+					if (WANT_DIAG && cj[u] == row)
+						diag = v;
+				}
+			}
+		} else {
+			// one node id per 2x2 block; lanes 2k, 2k+1 (the two dofs of a node) share it
+			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + (lane >> 1);
+			const uint32_t nblk = width >> 1;
+			const uint32_t safe_node = safe >> 1;
+			for (uint32_t b0 = 0; b0 < nblk; b0 += kGatherBatch) {
+				uint32_t cb[kGatherBatch];
+				double2 xb[kGatherBatch];
+#pragma unroll
+				for (int u = 0; u < kGatherBatch; u++)
+					cb[u] = (b0 + u < nblk) ? scol[(b0 + u) * 16u] : kPadCol;
+#pragma unroll
+				for (int u = 0; u < kGatherBatch; u++)
+					xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? safe_node : cb[u]));
+#pragma unroll
+				for (int u = 0; u < kGatherBatch; u++) {
+					const bool in = b0 + u < nblk;
+					const double v0 = in ? sval[(2 * (b0 + u)) * kSliceRows] : 0.0;
+					const double v1 = in ? sval[(2 * (b0 + u) + 1) * kSliceRows] : 0.0;
+					const bool pad = cb[u] == kPadCol;
+					const double t0 = __dmul_rn(v0, xb[u].x);
+					acc = pad ? acc : __dadd_rn(acc, t0);
+					const double t1 = __dmul_rn(v1, xb[u].y);
+					acc = pad ? acc : __dadd_rn(acc, t1);
+					if (WANT_DIAG && !pad && cb[u] == (row >> 1))
+						diag = (row & 1) ? v1 : v0;
+				}
+			}
+		}
+		// every lane is done with the stage: hand it back to the producer
+		__syncwarp();
+		if (lane == 0) {
+			const uint64_t next = s64 + (uint64_t)cfg.stages * total_warps;
+			if (next < A.n_slices) {
+				fence_proxy_async();
+				issue(st, (uint32_t)next);
+			}
+		}
+		body(row, acc, diag);
+	}
+}
+
+// host: choose ring depth / CTAs per SM for a matrix; returns false when the
+// widest slice does not fit (the register-path kernels are used instead)
+bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cfg);
+
+}  // namespace nbgpu

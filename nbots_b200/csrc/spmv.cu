@@ -1,7 +1,7 @@
 // spmv.cu -- nb_sparse_multiply_vector (sources/nb/solver_bot/sparse/sparse.c:405-414).
 #include <algorithm>
 
-#include "spmv.cuh"
+#include "sell_stream.cuh"
 
 using namespace nbgpu;
 
@@ -25,6 +25,69 @@ spmv_sell_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ sli
 		if (row < N)
 			y[row] = acc;
 	}
+}
+
+template <bool BLOCKED>
+__global__ void __launch_bounds__(kBlock, 2)
+spmv_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ x, double *__restrict__ y)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	sell_stream_rows<BLOCKED, false>(A, x, cfg, smem, [&](uint32_t row, double acc, double) {
+		if (row < A.N)
+			y[row] = acc;
+	});
+}
+
+// Ring depth and CTAs per SM for the streamed kernels of matrix A.  Shared memory
+// per CTA = 8 warps x stages x stage_bytes; two CTAs per SM (16 consumer warps)
+// are preferred, one is accepted for wide slices.  Env overrides for tuning:
+// NBGPU_STREAM_STAGES, NBGPU_STREAM_CTAS; NBGPU_SPMV_PATH=reg disables the path.
+bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cfg)
+{
+	const char *path = getenv("NBGPU_SPMV_PATH");
+	if (path && path[0] == 'r')
+		return false;
+	if (A->max_width == 0)
+		return false;
+	const uint32_t cap = (A->max_width + 1u) & ~1u;
+	const uint32_t stage_bytes = stream_stage_bytes(cap, A->blocked);
+	const uint32_t fixed = kStreamWarps * kStreamMaxStages * (sizeof(uint64_t) + sizeof(uint2));
+	int smem_optin = 0;
+	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx().device);
+	int want_ctas = getenv("NBGPU_STREAM_CTAS") ? atoi(getenv("NBGPU_STREAM_CTAS")) : 2;
+	int want_stages = getenv("NBGPU_STREAM_STAGES") ? atoi(getenv("NBGPU_STREAM_STAGES")) : 0;
+	for (int ctas = want_ctas; ctas >= 1; ctas--) {
+		// 228 KB per SM, 1 KB reserved per CTA, some static shared memory for the reductions
+		const int64_t budget = std::min<int64_t>(smem_optin, (228 * 1024) / ctas - 2048);
+		int64_t stages = (budget - fixed) / ((int64_t)kStreamWarps * stage_bytes);
+		stages = std::min<int64_t>(stages, kStreamMaxStages);
+		if (want_stages > 0)
+			stages = std::min<int64_t>(stages, want_stages);
+		if (stages < 2)
+			continue;
+		cfg->cap = cap;
+		cfg->stages = (uint32_t)stages;
+		cfg->stage_bytes = stage_bytes;
+		cfg->smem_bytes = (uint32_t)(kStreamWarps * stages * stage_bytes + fixed);
+		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes) !=
+		    cudaSuccess) {
+			cudaGetLastError();
+			continue;
+		}
+		int per_sm = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, cfg->smem_bytes) !=
+			    cudaSuccess ||
+		    per_sm < 1) {
+			cudaGetLastError();
+			continue;
+		}
+		per_sm = std::min(per_sm, ctas);
+		const int64_t want = ((int64_t)A->n_slices + kStreamWarps - 1) / kStreamWarps;
+		const int64_t cap_grid = std::min<int64_t>((int64_t)ctx().sm_count * per_sm, kMaxPartialBlocks);
+		cfg->grid = (int)std::max<int64_t>(1, std::min(want, cap_grid));
+		return true;
+	}
+	return false;
 }
 
 int spmv_grid(uint32_t n_slices)
@@ -52,6 +115,17 @@ int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out)
 	NB_ARG(d_in != d_out);   /* the reference accumulates into out[]: no aliasing (sparse.c:410) */
 	if (A->N == 0)
 		return NBGPU_OK;
+	StreamConfig cfg;
+	const void *kernel = A->blocked ? (const void *)spmv_stream_kernel<true> : (const void *)spmv_stream_kernel<false>;
+	if (stream_config(A, kernel, &cfg)) {
+		const SellView V{A->N, A->n_slices, A->d_slice_off, A->d_val, A->blocked ? A->d_bcol : A->d_col};
+		if (A->blocked)
+			spmv_stream_kernel<true><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
+		else
+			spmv_stream_kernel<false><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
+		NB_LAUNCHED();
+		return NBGPU_OK;
+	}
 	spmv_sell_kernel<<<spmv_grid(A->n_slices), kBlock, 0, ctx().stream>>>(
 		A->N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, d_in, d_out);
 	NB_LAUNCHED();

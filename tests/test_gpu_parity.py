@@ -88,20 +88,68 @@ def test_spmv_edge_cases(nbgpu_lib):
 
 # ------------------------------------------------------------------------ Krylov --
 
+@pytest.fixture
+def sequential_dots(nbgpu_lib):
+    capi.check(nbgpu_lib.nbgpu_set_reduction_order(1))
+    yield
+    capi.check(nbgpu_lib.nbgpu_set_reduction_order(0))
+
+
+@pytest.mark.parametrize("name", FEM_CASES + ["lap9_48"])
+def test_solvers_bit_identical_in_reference_order(nbgpu_lib, sequential_dots, name):
+    """With the dot products summed in the reference's (single-thread) order the whole solve is the
+    reference's, bit for bit: iterates, iteration count, tolerance_reached, return code."""
+    g = golden(name)
+    fem = "K_post" in g.files
+    A = api.Matrix.from_csr(g["rows_size"], g["cols"], g["K_post"] if fem else g["vals"])
+    b = g["F_post"] if fem else g["b"]
+    st, x, it, res = A.pcg_jacobi_host(b, tol=float(g["tol"]))
+    assert (st, it, res) == (int(g["pcg_status"]), int(g["pcg_iters"]), float(g["pcg_res"]))
+    assert np.array_equal(x, g["x"])
+    st, x, it, res = A.cg_host(b, tol=float(g["tol"]))
+    assert (st, it, res) == (int(g["cg_status"]), int(g["cg_iters"]), float(g["cg_res"]))
+    assert np.array_equal(x, g["x_cg"])
+
+
 @pytest.mark.parametrize("name", FEM_CASES)
 def test_pcg_jacobi_matches_reference(nbgpu_lib, name):
+    """Default (parallel-tree) reductions against the reference's run of its FEM driver's solver call
+    (x0 = 0, abs tol, max_iter = N)."""
     g = golden(name)
     A = api.Matrix.from_csr(g["rows_size"], g["cols"], g["K_post"])
-    st, x, it, res = A.pcg_jacobi_host(g["F_post"], tol=float(g["tol"]))
-    assert st == int(g["pcg_status"])
-    assert iters_close(it, int(g["pcg_iters"])), (it, int(g["pcg_iters"]))
-    assert rel_l2(x, g["x"]) <= TOL_VALUES
-    assert res <= float(g["tol"])
-    st, x, it, res = A.cg_host(g["F_post"], tol=float(g["tol"]))
-    if int(g["cg_status"]) == 0:
-        assert st == 0 and iters_close(it, int(g["cg_iters"])) and rel_l2(x, g["x_cg"]) <= 1e-8
+    b = g["F_post"]
+    st, x, it, res = A.pcg_jacobi_host(b, tol=float(g["tol"]))
+    assert st == int(g["pcg_status"]) and res <= float(g["tol"])
+    rel_tol_asked = float(g["tol"]) / np.linalg.norm(b)
+    if rel_tol_asked > 1e-14:
+        assert iters_close(it, int(g["pcg_iters"])), (it, int(g["pcg_iters"]))
+        assert rel_l2(x, g["x"]) <= TOL_VALUES
     else:
-        assert st == 1 and it == int(g["cg_iters"])      # ran into max_iter = N like the reference
+        # beam_cantilever (E = 2e11, prescribed displacement): the reference's absolute 1e-8 is a
+        # RELATIVE 5e-18, below what double precision can resolve.  The recurrence residual still
+        # reaches it, but how many iterations that takes is decided by rounding noise (SURVEY.md §7
+        # hard part (c)); only the reference-order mode above reproduces the count (801).  Here: the
+        # reference's own acceptance test, and the solution to the accuracy the system allows.
+        # measured on B200: 730-760 iterations (depends on the reduction tree) vs 801, and the
+        # fully converged fields agree to 4e-15.
+        u = np.sqrt((x.reshape(-1, 2) ** 2).sum(axis=1)).max()
+        assert abs(u - 1.00701e-1) < 1e-6                    # utest static_elasticity2D.c:118
+        assert rel_l2(x, g["x"]) <= TOL_VALUES
+        assert abs(it - int(g["pcg_iters"])) <= 0.15 * int(g["pcg_iters"])
+    # the well-posed form of the same solve (tol = 1e-8 |b|, SURVEY.md §8d): +-2 % and 1e-10
+    tol = 1e-8 * float(np.linalg.norm(b))
+    ost, ox, oit, ores = port.Csr(g["rows_size"], g["cols"], g["K_post"]).pcg_jacobi(b, tol=tol)
+    st, x, it, res = A.pcg_jacobi_host(b, tol=tol)
+    assert st == ost == 0 and iters_close(it, oit), (it, oit)
+    # Iterates stopped mid-convergence (true relative residual ~1e-8) carry the 1e-15 differences of
+    # the dot-product rounding amplified by ~sqrt(cond): 1.4e-10 on the beam (E = 2e11 next to the
+    # unit Dirichlet rows), <= 5e-11 elsewhere.  The stated 1e-10 is for converged fields (above).
+    assert rel_l2(x, ox) <= (1e-9 if name == "beam_cantilever_trg1000" else TOL_VALUES)
+    st, x, it, res = A.cg_host(b, tol=tol)
+    ost, ox, oit, ores = port.Csr(g["rows_size"], g["cols"], g["K_post"]).cg(b, tol=tol)
+    assert st == ost and iters_close(it, oit), (it, oit)
+    if ost == 0:
+        assert rel_l2(x, ox) <= (1e-9 if name == "beam_cantilever_trg1000" else TOL_VALUES)
 
 
 def test_pcg_semantics_on_laplacian(nbgpu_lib):
@@ -256,40 +304,63 @@ def test_strain_and_stress_bit_exact(nbgpu_lib, name):
 
 # ------------------------------------------------------------------------ driver --
 
-@pytest.mark.parametrize("name", FEM_CASES)
-def test_fem_driver_matches_reference(nbgpu_lib, name):
-    """nbgpu_fem_static_elasticity2d == nb_fem_compute_2D_Solid_Mechanics on the same inputs."""
-    g = golden(name)
+class _Desc(C.Structure):
+    _fields_ = [("N_nod", C.c_uint32), ("nod", capi.f64p), ("N_elems", C.c_uint32), ("npe", C.c_uint32),
+                ("adj", capi.u32p), ("N_edg", C.c_uint32), ("edg", capi.u32p), ("N_vtx", C.c_uint32),
+                ("vtx", capi.u32p), ("N_sgm", C.c_uint32), ("sgm_sizes", capi.u32p), ("sgm_nodes", capi.u32p)]
+
+
+class _Report(C.Structure):
+    _fields_ = [("N", C.c_uint32), ("nnz", C.c_uint64), ("iters", C.c_uint32), ("status", C.c_int32),
+                ("residual", C.c_double), ("ms", C.c_double * 6)]
+
+
+def run_driver(L, g, mode=capi.ASSEMBLY_GATHER):
+    """nbgpu_fem_static_elasticity2d on a golden case -> (status, report, displacement, strain)."""
     m = mesh_of(g)
-
-    class Desc(C.Structure):
-        _fields_ = [("N_nod", C.c_uint32), ("nod", capi.f64p), ("N_elems", C.c_uint32), ("npe", C.c_uint32),
-                    ("adj", capi.u32p), ("N_edg", C.c_uint32), ("edg", capi.u32p), ("N_vtx", C.c_uint32),
-                    ("vtx", capi.u32p), ("N_sgm", C.c_uint32), ("sgm_sizes", capi.u32p), ("sgm_nodes", capi.u32p)]
-
-    class Report(C.Structure):
-        _fields_ = [("N", C.c_uint32), ("nnz", C.c_uint64), ("iters", C.c_uint32), ("status", C.c_int32),
-                    ("residual", C.c_double), ("ms", C.c_double * 6)]
     p = lambda a, t: a.ctypes.data_as(t)  # noqa: E731
-    d = Desc(m.n_nod, p(m.nod, capi.f64p), m.n_elems, m.npe, p(m.adj, capi.u32p), m.n_edg, p(m.edg, capi.u32p),
-             m.vtx.size, p(m.vtx, capi.u32p), m.sgm_sizes.size, p(m.sgm_sizes, capi.u32p), p(m.sgm_nodes, capi.u32p))
+    d = _Desc(m.n_nod, p(m.nod, capi.f64p), m.n_elems, m.npe, p(m.adj, capi.u32p), m.n_edg, p(m.edg, capi.u32p),
+              m.vtx.size, p(m.vtx, capi.u32p), m.sgm_sizes.size, p(m.sgm_sizes, capi.u32p), p(m.sgm_nodes, capi.u32p))
     bcs, nbc = product_bcs(bc_records(g))
     ngp = 4 if m.kind else 1
     disp = np.zeros(2 * m.n_nod); strain = np.zeros(3 * ngp * m.n_elems)
     grav = (C.c_double * 2)(*g["gravity"])
     en = g["enabled"] if "enabled" in g.files else None
-    rep = Report()
-    f = nbgpu_lib.nbgpu_fem_static_elasticity2d
+    rep = _Report()
+    f = L.nbgpu_fem_static_elasticity2d
     f.restype = C.c_int
     st = f(C.byref(d), None, C.c_double(float(g["E"])), C.c_double(float(g["nu"])), C.c_double(float(g["density"])),
            C.c_uint32(nbc), bcs, C.c_int(int(g["self_weight"])), grav, C.c_int(int(g["analysis"])),
            C.c_double(float(g["thickness"])), None if en is None else en.ctypes.data_as(capi.u8p),
-           C.c_int(capi.ASSEMBLY_GATHER), C.c_double(float(g["tol"])), p(disp, capi.f64p), p(strain, capi.f64p),
-           C.byref(rep))
-    assert st == 0, nbgpu_lib.nbgpu_last_error()
+           C.c_int(mode), C.c_double(float(g["tol"])), p(disp, capi.f64p), p(strain, capi.f64p), C.byref(rep))
+    assert st == 0, L.nbgpu_last_error()
+    return st, rep, disp, strain
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_fem_driver_matches_reference(nbgpu_lib, name):
+    """nbgpu_fem_static_elasticity2d == nb_fem_compute_2D_Solid_Mechanics on the same inputs."""
+    g = golden(name)
+    st, rep, disp, strain = run_driver(nbgpu_lib, g)
     assert (rep.N, rep.nnz) == (g["rows_size"].size, g["cols"].size)
-    assert iters_close(rep.iters, int(g["pcg_iters"])) and rep.status == int(g["pcg_status"])
+    ill_posed = float(g["tol"]) / np.linalg.norm(g["F_post"]) < 1e-14      # see test_pcg_jacobi_matches_reference
+    budget = 0.15 * int(g["pcg_iters"]) if ill_posed else max(1, int(np.ceil(TOL_ITERS * int(g["pcg_iters"]))))
+    assert abs(rep.iters - int(g["pcg_iters"])) <= budget and rep.status == int(g["pcg_status"])
     assert rel_l2(disp, g["x"]) <= TOL_VALUES
     assert rel_l2(strain, g["strain"]) <= 1e-9
     if name == "beam_cantilever_trg1000":      # the reference's own assert (utest static_elasticity2D.c:118)
         assert abs(np.sqrt((disp.reshape(-1, 2) ** 2).sum(axis=1)).max() - 1.00701e-1) < 1e-6
+    # element-parallel assembly schedules feed the same solve
+    for mode in (capi.ASSEMBLY_ATOMIC, capi.ASSEMBLY_COLOR):
+        st, rep2, disp2, strain2 = run_driver(nbgpu_lib, g, mode)
+        assert rel_l2(disp2, g["x"]) <= TOL_VALUES
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_fem_driver_bit_identical_in_reference_order(nbgpu_lib, sequential_dots, name):
+    """Whole pipeline (pattern, assembly, BCs, PCG, strain) with reference-order dot products:
+    displacement, strain and iteration count are the reference's, bit for bit."""
+    g = golden(name)
+    st, rep, disp, strain = run_driver(nbgpu_lib, g)
+    assert (rep.iters, rep.status, rep.residual) == (int(g["pcg_iters"]), int(g["pcg_status"]), float(g["pcg_res"]))
+    assert np.array_equal(disp, g["x"]) and np.array_equal(strain, g["strain"])
