@@ -228,13 +228,15 @@ def run_ours(args):
                 C.byref(it), C.byref(res), 1)
         dt = time.perf_counter() - t0
         assert st == 0, capi.lib().nbgpu_last_error()
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"e2e call {k}: {dt*1e3:.1f} ms, iters {it.value}", file=sys.stderr)
         if k >= 2:
             e2e_times.append(dt)
         e2e_iters = it.value
-    e2e_value = N * e2e_iters / float(np.mean(e2e_times))
+    e2e_value = N * e2e_iters / float(np.median(e2e_times))
     assert np.array_equal(x_host, x_resident), "e2e and resident solves must be the same computation"
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz + 16 * N),
-           "d2h_bytes_per_step": int(8 * N), "ms_per_step": round(float(np.mean(e2e_times)) * 1e3, 2),
+           "d2h_bytes_per_step": int(8 * N), "ms_per_step": round(float(np.median(e2e_times)) * 1e3, 2),
            "entry_point": "nb_sparse_solve_CG_precond_Jacobi (libnbots_b200.so), host nb_sparse_t"}
 
     cpu = cpu_baseline(m, b, tol, x_resident, vals, d_F_host=b) if not args.no_cpu_baseline else None

@@ -57,6 +57,8 @@ int nbgpu_sync(void);
 const char *nbgpu_last_error(void);
 /* the cudaStream_t every kernel of this library is launched on */
 void *nbgpu_stream(void);
+/* one-line JSON description of the bound device (SMs, L2, carve-outs, HBM) */
+int nbgpu_device_info(char *buf, size_t len);
 /* number of kernels this library has launched so far (for `gpu_launches`) */
 uint64_t nbgpu_launch_count(void);
 

@@ -286,3 +286,10 @@ def sync():
 
 def launch_count() -> int:
     return int(lib().nbgpu_launch_count())
+
+
+def device_info() -> dict:
+    import json
+    buf = C.create_string_buffer(1024)
+    check(lib().nbgpu_device_info(buf, 1024))
+    return json.loads(buf.value.decode())

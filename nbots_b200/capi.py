@@ -54,6 +54,7 @@ SIGNATURES = {
     "nbgpu_last_error": (C.c_char_p, []),
     "nbgpu_stream": (C.c_void_p, []),
     "nbgpu_launch_count": (C.c_uint64, []),
+    "nbgpu_device_info": (C.c_int, [C.c_char_p, C.c_size_t]),
     "nbgpu_malloc": (C.c_int, [vpp, C.c_size_t]),
     "nbgpu_free": (C.c_int, [C.c_void_p]),
     "nbgpu_memset": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),

@@ -88,6 +88,19 @@ int ensure_workspace(size_t bytes);
 #ifdef __CUDACC__
 namespace nbgpu {
 
+// Programmatic dependent launch (PDL).  A kernel launched with the
+// programmatic-stream-serialization attribute may start while its predecessor
+// in the stream is still draining; it must not touch anything the predecessor
+// produces before pdl_wait().  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

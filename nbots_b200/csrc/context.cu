@@ -164,6 +164,27 @@ int nbgpu_device_count(void)
 	return count;
 }
 
+int nbgpu_device_info(char *buf, size_t len)
+{
+	NB_INIT();
+	NB_ARG(buf != nullptr && len > 0);
+	cudaDeviceProp prop;
+	NB_CUDA(cudaGetDeviceProperties(&prop, g_ctx.device));
+	int persist = 0, window = 0, smem_optin = 0;
+	cudaDeviceGetAttribute(&persist, cudaDevAttrMaxPersistingL2CacheSize, g_ctx.device);
+	cudaDeviceGetAttribute(&window, cudaDevAttrMaxAccessPolicyWindowSize, g_ctx.device);
+	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_ctx.device);
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	snprintf(buf, len,
+		 "{\"name\": \"%s\", \"cc\": \"%d.%d\", \"sms\": %d, \"l2_bytes\": %d, "
+		 "\"max_persisting_l2_bytes\": %d, \"max_access_policy_window_bytes\": %d, "
+		 "\"smem_per_block_optin\": %d, \"hbm_total_bytes\": %zu, \"hbm_free_bytes\": %zu}",
+		 prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.l2CacheSize, persist, window,
+		 smem_optin, total_b, free_b);
+	return NBGPU_OK;
+}
+
 int nbgpu_sync(void)
 {
 	NB_INIT();

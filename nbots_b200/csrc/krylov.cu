@@ -7,9 +7,9 @@
 // One reference iteration is three OpenMP loops separated by two scalar
 // reductions; here it is three kernels and the scalars never visit the host:
 //
-//   K1  iter_spmv    w = A p,  pw = p.w          (reduction fused in the SpMV)
-//   K2  iter_update  x += a p, g += a w, q = g/diag, gq' = g.q, gg' = g.g
-//   K3  iter_dir     p = -q + b p
+//   K1  spmv     w = A p,  pw = p.w          (reduction fused in the SpMV)
+//   K2  update   x += a p, g += a w, q = g/diag, gq' = g.q, gg' = g.g
+//   K3  dir      p = -q + b p
 //
 // a = gq/pw and b = gq'/gq are recomputed by every thread from the reduced
 // dots kept in a small state block in HBM.  The reference's pass 1 also
@@ -26,9 +26,25 @@
 // enqueues chunks of iterations and polls a `done` flag one chunk behind, so
 // the GPU never waits for the host.  Kernels of iterations enqueued past
 // convergence return immediately.
+//
+// B200 specifics:
+//   * K1 streams the matrix through shared memory with TMA bulk copies
+//     (sell_stream.cuh); a register-path K1 is kept for matrices whose widest
+//     slice does not fit a stage.
+//   * All kernels are launched with programmatic dependent launch: the next
+//     kernel's CTAs become resident while the current one runs, K1 already
+//     requests its first matrix stages and K2/K3 preload the operands the
+//     running kernel does not write, each before `griddepcontrol.wait`.  Every
+//     kernel releases its dependents only AFTER its own wait, so a kernel's
+//     pre-wait section overlaps its immediate predecessor only.
+//   * When the work vectors fit the persisting-L2 carve-out they are pinned
+//     there for the duration of the solve (access-policy window on the stream,
+//     everything else -- the matrix -- marked streaming), so only the matrix
+//     comes from HBM in steady state.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "sell_stream.cuh"
@@ -54,7 +70,66 @@ constexpr uint32_t kChunkIters = 32;
 
 __device__ __forceinline__ uint32_t gate_slot(uint32_t k) { return k == 0 ? 0u : (k - 1) % 3u; }
 
-// g = A x - b, diag, q = g / diag, p = -q, gg = g.g, gq = g.q   (init, :33-43)
+// The loop test of iteration k (:45).  Returns true when the iteration runs;
+// otherwise records the exit (once) and makes every later kernel a no-op.
+__device__ __forceinline__ bool iteration_gate(uint32_t k, KrylovState *st)
+{
+	if (*(volatile int32_t *)&st->done)
+		return false;
+	const double gg = st->gg[gate_slot(k)];
+	if (gg > st->tol2 && k < st->max_iter)
+		return true;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		st->k_final = k;
+		st->gg_final = gg;
+		__threadfence();
+		st->done = 1;
+	}
+	return false;
+}
+
+template <bool JACOBI>
+__device__ __forceinline__ void init_row(uint32_t row, double acc, double d, const double *__restrict__ b,
+					 double *__restrict__ g, double *__restrict__ p, double *__restrict__ q,
+					 double *__restrict__ diag, double (&dots)[2])
+{
+	// g = A x - b, q = g / Aii, p = -q   (:33-43)
+	const double gi = __dsub_rn(acc, b[row]);
+	g[row] = gi;
+	dots[0] = __dadd_rn(dots[0], __dmul_rn(gi, gi));
+	if (JACOBI) {
+		const double qi = __ddiv_rn(gi, d);
+		diag[row] = d;
+		q[row] = qi;
+		p[row] = -qi;
+		dots[1] = __dadd_rn(dots[1], __dmul_rn(gi, qi));
+	} else {
+		p[row] = -gi;
+	}
+}
+
+template <bool JACOBI>
+__device__ __forceinline__ void init_finish(double (&dots)[2], double *partials, KrylovState *st)
+{
+	if (!partials)
+		return;   // reference-order mode: seq_dot_kernel follows
+	double tot[2];
+	if (grid_reduce<2>(dots, partials, &st->ticket, tot) && threadIdx.x == 0) {
+		st->gg[0] = tot[0];
+		st->gq[0] = JACOBI ? tot[1] : tot[0];
+	}
+}
+
+__device__ __forceinline__ void spmv_finish(double (&dots)[1], double *partials, KrylovState *st)
+{
+	if (!partials)
+		return;
+	double tot[1];
+	if (grid_reduce<1>(dots, partials, &st->ticket, tot) && threadIdx.x == 0)
+		st->pw = tot[0];
+}
+
+// ---- register path (fallback for very wide slices) -----------------------------
 template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock, 4)
 krylov_init_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
@@ -63,6 +138,8 @@ krylov_init_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ s
 		   double *__restrict__ p, double *__restrict__ q, double *__restrict__ diag,
 		   double *partials, KrylovState *st)
 {
+	pdl_wait();
+	pdl_launch_dependents();
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	double dots[2] = {0.0, 0.0};
@@ -73,52 +150,22 @@ krylov_init_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ s
 		double d = 0.0;
 		const double acc = sell_row_times<kIterUnroll, JACOBI>(val, col, off, width, lane, row,
 								       min(row, N - 1), x, &d);
-		if (row < N) {
-			const double gi = __dsub_rn(acc, b[row]);
-			g[row] = gi;
-			dots[0] = __dadd_rn(dots[0], __dmul_rn(gi, gi));
-			if (JACOBI) {
-				const double qi = __ddiv_rn(gi, d);
-				diag[row] = d;
-				q[row] = qi;
-				p[row] = -qi;
-				dots[1] = __dadd_rn(dots[1], __dmul_rn(gi, qi));
-			} else {
-				p[row] = -gi;
-			}
-		}
+		if (row < N)
+			init_row<JACOBI>(row, acc, d, b, g, p, q, diag, dots);
 	}
-	if (!partials)
-		return;
-	double tot[2];
-	if (grid_reduce<2>(dots, partials, &st->ticket, tot) && threadIdx.x == 0) {
-		st->gg[0] = tot[0];
-		st->gq[0] = JACOBI ? tot[1] : tot[0];
-	}
+	init_finish<JACOBI>(dots, partials, st);
 }
 
-// K1: gate, w = A p, pw = p.w   (:45, :50-58)
 __global__ void __launch_bounds__(kBlock, 4)
 krylov_spmv_kernel(uint32_t k, uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
 		   const double *__restrict__ val, const uint32_t *__restrict__ col,
 		   const double *__restrict__ p, double *__restrict__ w, double *partials,
 		   KrylovState *st)
 {
-	if (*(volatile int32_t *)&st->done)
+	pdl_wait();
+	pdl_launch_dependents();
+	if (!iteration_gate(k, st))
 		return;
-	{
-		const double gg = st->gg[gate_slot(k)];
-		const bool active = gg > st->tol2 && k < st->max_iter;
-		if (!active) {
-			if (blockIdx.x == 0 && threadIdx.x == 0) {
-				st->k_final = k;
-				st->gg_final = gg;
-				__threadfence();
-				st->done = 1;
-			}
-			return;
-		}
-	}
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	double dots[1] = {0.0};
@@ -133,14 +180,10 @@ krylov_spmv_kernel(uint32_t k, uint32_t N, uint32_t n_slices, const uint32_t *__
 			dots[0] = __dadd_rn(dots[0], __dmul_rn(__ldg(p + row), acc));
 		}
 	}
-	if (!partials)
-		return;
-	double tot[1];
-	if (grid_reduce<1>(dots, partials, &st->ticket, tot) && threadIdx.x == 0)
-		st->pw = tot[0];
+	spmv_finish(dots, partials, st);
 }
 
-// ---- the same two kernels with the matrix streamed through shared memory (sell_stream.cuh) ----
+// ---- streamed path: the matrix goes through shared memory (sell_stream.cuh) -----
 template <bool JACOBI, bool BLOCKED>
 __global__ void __launch_bounds__(kBlock, 2)
 krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ b,
@@ -149,29 +192,13 @@ krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[2] = {0.0, 0.0};
-	sell_stream_rows<BLOCKED, JACOBI>(A, x, cfg, smem, [&](uint32_t row, double acc, double d) {
-		if (row < A.N) {
-			const double gi = __dsub_rn(acc, b[row]);
-			g[row] = gi;
-			dots[0] = __dadd_rn(dots[0], __dmul_rn(gi, gi));
-			if (JACOBI) {
-				const double qi = __ddiv_rn(gi, d);
-				diag[row] = d;
-				q[row] = qi;
-				p[row] = -qi;
-				dots[1] = __dadd_rn(dots[1], __dmul_rn(gi, qi));
-			} else {
-				p[row] = -gi;
-			}
-		}
-	});
-	if (!partials)
-		return;
-	double tot[2];
-	if (grid_reduce<2>(dots, partials, &st->ticket, tot) && threadIdx.x == 0) {
-		st->gg[0] = tot[0];
-		st->gq[0] = JACOBI ? tot[1] : tot[0];
-	}
+	sell_stream_rows<BLOCKED, JACOBI>(
+		A, x, cfg, smem, [] { return true; },
+		[&](uint32_t row, double acc, double d, double) {
+			if (row < A.N)
+				init_row<JACOBI>(row, acc, d, b, g, p, q, diag, dots);
+		});
+	init_finish<JACOBI>(dots, partials, st);
 }
 
 template <bool BLOCKED>
@@ -180,59 +207,67 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, const double
 			  double *__restrict__ w, double *partials, KrylovState *st)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	if (*(volatile int32_t *)&st->done)
-		return;
-	{
-		const double gg = st->gg[gate_slot(k)];
-		const bool active = gg > st->tol2 && k < st->max_iter;
-		if (!active) {
-			if (blockIdx.x == 0 && threadIdx.x == 0) {
-				st->k_final = k;
-				st->gg_final = gg;
-				__threadfence();
-				st->done = 1;
-			}
-			return;
-		}
-	}
 	double dots[1] = {0.0};
-	sell_stream_rows<BLOCKED, false>(A, p, cfg, smem, [&](uint32_t row, double acc, double) {
-		if (row < A.N) {
-			w[row] = acc;
-			dots[0] = __dadd_rn(dots[0], __dmul_rn(__ldg(p + row), acc));
-		}
-	});
-	if (!partials)
+	bool active = true;
+	sell_stream_rows<BLOCKED, false>(
+		A, p, cfg, smem,
+		[&] {
+			// a function of (k, state) only: the whole grid takes the same branch
+			active = iteration_gate(k, st);
+			return active;
+		},
+		[&](uint32_t row, double acc, double, double p_row) {
+			if (row < A.N) {
+				w[row] = acc;
+				dots[0] = __dadd_rn(dots[0], __dmul_rn(p_row, acc));
+			}
+		});
+	if (!active)
 		return;
-	double tot[1];
-	if (grid_reduce<1>(dots, partials, &st->ticket, tot) && threadIdx.x == 0)
-		st->pw = tot[0];
+	spmv_finish(dots, partials, st);
 }
 
 // K2: x += a p, g += a w, q = g / diag, gq' = g.q, gg' = g.g   (:59-68)
-// Two elements per thread and trip: all ten loads are issued before the first use.
+// Two elements per thread and trip, every load of a trip issued before the first
+// use; the first trip's p, x, g, diag are loaded before the dependency wait (the
+// SpMV kernel running ahead of us only writes w and the scalars).
 template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock)
 krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const double *__restrict__ w,
 		     const double *__restrict__ diag, double *__restrict__ x, double *__restrict__ g,
 		     double *__restrict__ q, double *partials, KrylovState *st)
 {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
+	double p0 = 0, x0 = 0, g0 = 0, d0 = 1, p1 = 0, x1 = 0, g1 = 0, d1 = 1;
+	if (base < N) {
+		const uint32_t j1 = base + stride < N ? base + stride : base;
+		p0 = p[base]; x0 = x[base]; g0 = g[base];
+		p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+		if (JACOBI) {
+			d0 = diag[base];
+			d1 = diag[j1];
+		}
+	}
+	pdl_wait();
+	pdl_launch_dependents();
 	if (*(volatile int32_t *)&st->done)
 		return;
 	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);
 	double dots[2] = {0.0, 0.0};
-	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < N; i0 += 2 * stride) {
+	for (uint32_t i0 = base; i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
-		const double p0 = p[i0], w0 = w[i0], x0 = x[i0], g0 = g[i0];
-		const double p1 = p[j1], w1 = w[j1], x1 = x[j1], g1 = g[j1];
-		double d0 = 1.0, d1 = 1.0;
-		if (JACOBI) {
-			d0 = diag[i0];
-			d1 = diag[j1];
+		if (i0 != base) {
+			p0 = p[i0]; x0 = x[i0]; g0 = g[i0];
+			p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+			if (JACOBI) {
+				d0 = diag[i0];
+				d1 = diag[j1];
+			}
 		}
+		const double w0 = w[i0], w1 = w[j1];
 		const double gn0 = __dadd_rn(g0, __dmul_rn(alpha, w0));
 		const double gn1 = __dadd_rn(g1, __dmul_rn(alpha, w1));
 		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
@@ -263,20 +298,33 @@ krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const
 	}
 }
 
-// K3: p = -q + b p   (:70-74); plain CG passes q == g
+// K3: p = -q + b p   (:70-74); plain CG passes q == g.  p is preloaded before the
+// dependency wait (the update kernel ahead of us does not write it).
 __global__ void __launch_bounds__(kBlock)
 krylov_dir_kernel(uint32_t k, uint32_t N, const double *__restrict__ q, double *__restrict__ p,
 		  const KrylovState *st)
 {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
+	double p0 = 0, p1 = 0;
+	if (base < N) {
+		p0 = p[base];
+		p1 = p[base + stride < N ? base + stride : base];
+	}
+	pdl_wait();
+	pdl_launch_dependents();
 	if (*(volatile const int32_t *)&st->done)
 		return;
 	const double beta = __ddiv_rn(st->gq[(k + 1) & 1], st->gq[k & 1]);
-	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < N; i0 += 2 * stride) {
+	for (uint32_t i0 = base; i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
-		const double q0 = q[i0], p0 = p[i0], q1 = q[j1], p1 = p[j1];
+		if (i0 != base) {
+			p0 = p[i0];
+			p1 = p[j1];
+		}
+		const double q0 = q[i0], q1 = q[j1];
 		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, p0));
 		if (has1)
 			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
@@ -317,6 +365,8 @@ __global__ void seq_dot_kernel(uint32_t N, const double *__restrict__ a1, const 
 	}
 }
 
+// ---- host ------------------------------------------------------------------------
+
 // Persistent grid of one kernel: exactly the number of CTAs that are resident at
 // once (SMs x occupancy), so the grid-stride loops run as a single full wave.
 template <typename Kernel>
@@ -331,14 +381,31 @@ int resident_grid(Kernel kernel, int64_t want_blocks)
 	return (int)std::max<int64_t>(1, std::min(want_blocks, cap));
 }
 
-bool g_seq_dots = false;
+// kernel launch with (optionally) the programmatic-dependent-launch attribute
+template <typename... KArgs, typename... Args>
+cudaError_t launch(bool pdl, void (*kernel)(KArgs...), int grid, size_t smem, Args &&...args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid);
+	cfg.blockDim = dim3(kBlock);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = ctx().stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl ? 1 : 0;
+	ctx().launches++;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
+bool g_seq_dots = false;
 cudaEvent_t g_poll_ev[2] = {nullptr, nullptr};
 
 // Optional per-kernel timing (nbgpu_krylov_profile): CUDA events around each of
 // the three kernels for the first kProfIters iterations of a solve, on the
-// stream the kernels run on.  Off by default; bench.py uses it in a separate,
-// untimed-for-throughput solve to get the live duration of the dominant kernel.
+// stream the kernels run on.  Off by default; bench.py uses it in a separate
+// solve to get the live duration of the dominant kernel.
 constexpr uint32_t kProfIters = 256;
 bool g_prof_on = false;
 std::vector<cudaEvent_t> g_prof_ev;    // 4 events per iteration
@@ -346,25 +413,59 @@ uint32_t g_prof_recorded = 0;
 double g_prof_ms[3] = {0, 0, 0};
 uint32_t g_prof_n = 0;
 
-int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_iter, double tol,
-	  uint32_t *niter, double *tol_reached, bool jacobi)
+// Pin [ptr, ptr+bytes) in the persisting-L2 carve-out for kernels on the stream,
+// mark everything else streaming.  Returns whether a window was installed.
+bool l2_pin(void *ptr, size_t bytes)
 {
-	NB_INIT();
-	NB_ARG(A != nullptr && d_b != nullptr && d_x != nullptr);
+	if (getenv("NBGPU_NO_L2_PIN"))
+		return false;
+	Context &c = ctx();
+	int max_persist = 0, max_window = 0;
+	cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
+	cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
+	if (max_persist <= 0 || max_window <= 0 || bytes == 0 || bytes > (size_t)max_window ||
+	    bytes > (size_t)max_persist)
+		return false;   // vectors larger than the carve-out: leave the L2 to its own policy
+	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	v.accessPolicyWindow.base_ptr = ptr;
+	v.accessPolicyWindow.num_bytes = bytes;
+	v.accessPolicyWindow.hitRatio = 1.0f;
+	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	if (cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return true;
+}
+
+void l2_unpin()
+{
+	Context &c = ctx();
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	v.accessPolicyWindow.num_bytes = 0;
+	cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &v);
+	cudaCtxResetPersistingL2Cache();
+	cudaGetLastError();
+}
+
+int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_iter, double tol,
+	       uint32_t *niter, double *tol_reached, bool jacobi)
+{
 	Context &c = ctx();
 	const uint32_t N = A->N;
-	if (N == 0) {
-		if (niter)
-			*niter = 0;
-		if (tol_reached)
-			*tol_reached = 0.0;
-		return NBGPU_OK;
-	}
-	// the reference allocates g,p,q,w,Aii in one block (:24-30); same here, grow-only
-	const size_t n_vec = jacobi ? 5 : 3;
-	NB_TRY(ensure_workspace(n_vec * (size_t)N * sizeof(double)));
-	double *g = c.ws, *p = g + N, *w = p + N;
-	double *q = jacobi ? w + N : g, *diag = jacobi ? q + N : nullptr;
+	// the reference allocates g,p,q,w,Aii in one block (:24-30); same here, grow-only.
+	// A private copy of x lives in the same block so that one L2 window covers every
+	// vector the iteration touches; it is copied in and out around the loop.
+	const size_t Np = ((size_t)N + 1) & ~(size_t)1;   // keep every vector 16-byte aligned
+	double *xw = c.ws, *g = xw + Np, *p = g + Np, *w = p + Np;
+	double *q = jacobi ? w + Np : g, *diag = jacobi ? q + Np : nullptr;
 	if (!c.dev_state) {
 		NB_CUDA(cudaMalloc(&c.dev_state, sizeof(KrylovState)));
 		NB_CUDA(cudaMallocHost(&c.host_state, 4 * sizeof(KrylovState)));
@@ -377,12 +478,16 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 	hst[2].tol2 = tol * tol;
 	hst[2].max_iter = max_iter;
 	NB_CUDA(cudaMemcpyAsync(st, &hst[2], sizeof(KrylovState), cudaMemcpyHostToDevice, c.stream));
+	NB_CUDA(cudaMemcpyAsync(xw, d_x, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 
 	const int64_t slice_blocks = ((int64_t)A->n_slices * 32 + kBlock - 1) / kBlock;
 	const int64_t vec_blocks = ((int64_t)N + 2 * kBlock - 1) / (2 * kBlock);
 	const int igrid = jacobi ? resident_grid(krylov_init_kernel<true>, slice_blocks)
 				 : resident_grid(krylov_init_kernel<false>, slice_blocks);
 	const int sgrid = resident_grid(krylov_spmv_kernel, slice_blocks);
+	const int ugrid = jacobi ? resident_grid(krylov_update_kernel<true>, vec_blocks)
+				 : resident_grid(krylov_update_kernel<false>, vec_blocks);
+	const int dgrid = resident_grid(krylov_dir_kernel, vec_blocks);
 	// streamed (TMA) path: same kernels, matrix staged through shared memory
 	const SellView V{N, A->n_slices, A->d_slice_off, A->d_val, A->blocked ? A->d_bcol : A->d_col};
 	StreamConfig scfg, icfg;
@@ -393,33 +498,32 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 				: (A->blocked ? (const void *)krylov_init_stream_kernel<false, true>
 					      : (const void *)krylov_init_stream_kernel<false, false>);
 	const bool stream = stream_config(A, sk, &scfg) && stream_config(A, ik, &icfg);
-	const int ugrid = jacobi ? resident_grid(krylov_update_kernel<true>, vec_blocks)
-				 : resident_grid(krylov_update_kernel<false>, vec_blocks);
-	const int dgrid = resident_grid(krylov_dir_kernel, vec_blocks);
 	const bool seq = g_seq_dots;
+	const bool pdl = !seq && !getenv("NBGPU_NO_PDL");
 	double *partials = seq ? nullptr : c.partials;
+
+	cudaError_t e;
 	if (stream) {
 		if (jacobi && A->blocked)
-			krylov_init_stream_kernel<true, true><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
-				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
+			e = launch(false, krylov_init_stream_kernel<true, true>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
+				   xw, g, p, q, diag, partials, st);
 		else if (jacobi)
-			krylov_init_stream_kernel<true, false><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
-				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
+			e = launch(false, krylov_init_stream_kernel<true, false>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
+				   xw, g, p, q, diag, partials, st);
 		else if (A->blocked)
-			krylov_init_stream_kernel<false, true><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
-				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
+			e = launch(false, krylov_init_stream_kernel<false, true>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
+				   xw, g, p, q, diag, partials, st);
 		else
-			krylov_init_stream_kernel<false, false><<<icfg.grid, kBlock, icfg.smem_bytes, c.stream>>>(
-				V, icfg, d_b, d_x, g, p, q, diag, partials, st);
-	} else if (jacobi)
-		krylov_init_kernel<true><<<igrid, kBlock, 0, c.stream>>>(
-			N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, d_b, d_x, g, p, q, diag,
-			partials, st);
-	else
-		krylov_init_kernel<false><<<igrid, kBlock, 0, c.stream>>>(
-			N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, d_b, d_x, g, p, q, diag,
-			partials, st);
-	NB_LAUNCHED();
+			e = launch(false, krylov_init_stream_kernel<false, false>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
+				   xw, g, p, q, diag, partials, st);
+	} else if (jacobi) {
+		e = launch(false, krylov_init_kernel<true>, igrid, 0, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col,
+			   d_b, xw, g, p, q, diag, partials, st);
+	} else {
+		e = launch(false, krylov_init_kernel<false>, igrid, 0, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col,
+			   d_b, xw, g, p, q, diag, partials, st);
+	}
+	NB_CUDA(e);
 	if (seq) {
 		seq_dot_kernel<<<1, 32, 0, c.stream>>>(N, g, g, &st->gg[0], jacobi ? g : nullptr, q, &st->gq[0], st);
 		NB_LAUNCHED();
@@ -428,8 +532,8 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 	g_prof_recorded = 0;
 	if (g_prof_on && g_prof_ev.empty()) {
 		g_prof_ev.resize(4 * kProfIters);
-		for (auto &e : g_prof_ev)
-			NB_CUDA(cudaEventCreate(&e));
+		for (auto &ev : g_prof_ev)
+			NB_CUDA(cudaEventCreate(&ev));
 	}
 	uint32_t k = 0;
 	int slot = 0;
@@ -442,15 +546,15 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k], c.stream));
 			if (stream && A->blocked)
-				krylov_spmv_stream_kernel<true><<<scfg.grid, kBlock, scfg.smem_bytes, c.stream>>>(
-					k, V, scfg, p, w, partials, st);
+				e = launch(pdl, krylov_spmv_stream_kernel<true>, scfg.grid, scfg.smem_bytes, k, V, scfg, p, w,
+					   partials, st);
 			else if (stream)
-				krylov_spmv_stream_kernel<false><<<scfg.grid, kBlock, scfg.smem_bytes, c.stream>>>(
-					k, V, scfg, p, w, partials, st);
+				e = launch(pdl, krylov_spmv_stream_kernel<false>, scfg.grid, scfg.smem_bytes, k, V, scfg, p, w,
+					   partials, st);
 			else
-				krylov_spmv_kernel<<<sgrid, kBlock, 0, c.stream>>>(
-					k, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, p, w, partials, st);
-			NB_LAUNCHED();
+				e = launch(pdl, krylov_spmv_kernel, sgrid, 0, k, N, A->n_slices, A->d_slice_off, A->d_val,
+					   A->d_col, p, w, partials, st);
+			NB_CUDA(e);
 			if (seq) {
 				seq_dot_kernel<<<1, 32, 0, c.stream>>>(N, p, w, &st->pw, nullptr, nullptr, nullptr, st);
 				NB_LAUNCHED();
@@ -458,12 +562,10 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 1], c.stream));
 			if (jacobi)
-				krylov_update_kernel<true><<<ugrid, kBlock, 0, c.stream>>>(
-					k, N, p, w, diag, d_x, g, q, partials, st);
+				e = launch(pdl, krylov_update_kernel<true>, ugrid, 0, k, N, p, w, diag, xw, g, q, partials, st);
 			else
-				krylov_update_kernel<false><<<ugrid, kBlock, 0, c.stream>>>(
-					k, N, p, w, diag, d_x, g, q, partials, st);
-			NB_LAUNCHED();
+				e = launch(pdl, krylov_update_kernel<false>, ugrid, 0, k, N, p, w, diag, xw, g, q, partials, st);
+			NB_CUDA(e);
 			if (seq) {
 				seq_dot_kernel<<<1, 32, 0, c.stream>>>(N, g, g, &st->gg[(k + 1) % 3u], jacobi ? g : nullptr,
 								       q, &st->gq[(k + 1) & 1], st);
@@ -471,8 +573,7 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 			}
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 2], c.stream));
-			krylov_dir_kernel<<<dgrid, kBlock, 0, c.stream>>>(k, N, q, p, st);
-			NB_LAUNCHED();
+			NB_CUDA(launch(pdl, krylov_dir_kernel, dgrid, 0, k, N, q, p, st));
 			if (prof) {
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 3], c.stream));
 				g_prof_recorded = k + 1;
@@ -480,9 +581,8 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 		}
 		if (k == max_iter) {
 			// the loop test that ends the reference's while at k == max_iter
-			krylov_spmv_kernel<<<1, kBlock, 0, c.stream>>>(
-				k, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, p, w, c.partials, st);
-			NB_LAUNCHED();
+			NB_CUDA(launch(false, krylov_spmv_kernel, 1, 0, k, N, A->n_slices, A->d_slice_off, A->d_val,
+				       A->d_col, p, w, partials, st));
 		}
 		NB_CUDA(cudaMemcpyAsync(&hst[slot], st, sizeof(KrylovState), cudaMemcpyDeviceToHost, c.stream));
 		NB_CUDA(cudaEventRecord(g_poll_ev[slot], c.stream));
@@ -497,6 +597,7 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 			finished = true;
 		slot ^= 1;
 	}
+	NB_CUDA(cudaMemcpyAsync(d_x, xw, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 	NB_CUDA(cudaMemcpyAsync(&hst[3], st, sizeof(KrylovState), cudaMemcpyDeviceToHost, c.stream));
 	NB_CUDA(cudaStreamSynchronize(c.stream));
 	if (!hst[3].done) {
@@ -523,6 +624,28 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 	return (hst[3].gg_final > hst[3].tol2) ? NBGPU_NOT_CONVERGED : NBGPU_OK;
 }
 
+int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_iter, double tol,
+	  uint32_t *niter, double *tol_reached, bool jacobi)
+{
+	NB_INIT();
+	NB_ARG(A != nullptr && d_b != nullptr && d_x != nullptr);
+	if (A->N == 0) {
+		if (niter)
+			*niter = 0;
+		if (tol_reached)
+			*tol_reached = 0.0;
+		return NBGPU_OK;
+	}
+	const size_t Np = ((size_t)A->N + 1) & ~(size_t)1;
+	const size_t ws_bytes = (jacobi ? 6 : 4) * Np * sizeof(double);
+	NB_TRY(ensure_workspace(ws_bytes));
+	const bool pinned = l2_pin(ctx().ws, ws_bytes);
+	const int status = solve_impl(A, d_b, d_x, max_iter, tol, niter, tol_reached, jacobi);
+	if (pinned)
+		l2_unpin();
+	return status;
+}
+
 int solve_host(const nbgpu_matrix_t *A, const double *b, double *x, uint32_t max_iter, double tol,
 	       uint32_t *niter, double *tol_reached, bool jacobi)
 {
@@ -530,9 +653,10 @@ int solve_host(const nbgpu_matrix_t *A, const double *b, double *x, uint32_t max
 	NB_ARG(A != nullptr && b != nullptr && x != nullptr);
 	Context &c = ctx();
 	const size_t bytes = (size_t)A->N * sizeof(double);
+	const size_t Np = ((size_t)A->N + 1) & ~(size_t)1;
 	double *d_b = nullptr, *d_x = nullptr;
-	NB_TRY(nbgpu_malloc((void **)&d_b, 2 * bytes));
-	d_x = d_b + A->N;
+	NB_TRY(nbgpu_malloc((void **)&d_b, 2 * Np * sizeof(double)));
+	d_x = d_b + Np;
 	int st = NBGPU_OK;
 	if (cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, c.stream) != cudaSuccess ||
 	    cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, c.stream) != cudaSuccess) {

@@ -111,12 +111,21 @@ struct SellView {
 	const uint32_t *col;    // per-entry column ids, or per-block node ids when BLOCKED
 };
 
-// Runs `body(row, acc, diag)` for every row of the slices this warp owns
+// Runs `body(row, acc, diag, x_row)` for every row of the slices this warp owns
 // (slices warp, warp + total_warps, ...), acc = sum_j A[row][j] x[col_j] in
-// ascending column order with separately rounded products and sums.
-template <bool BLOCKED, bool WANT_DIAG, typename Body>
+// ascending column order with separately rounded products and sums.  diag is
+// A[row][row] (WANT_DIAG) and x_row is x[row]: both are picked up from the
+// diagonal entry's column while it passes by (FEM rows always store their
+// diagonal), which saves the solvers a second dependent load per row.
+//
+// The matrix never changes during a solve, so the first stages are requested
+// BEFORE the programmatic-dependency wait: the bulk copies of this kernel
+// overlap the tail of the previous kernel in the stream.  `gate()` is evaluated
+// after the wait (it may read what the predecessor wrote); when it returns
+// false the warp only drains its in-flight copies and leaves.
+template <bool BLOCKED, bool WANT_DIAG, typename Gate, typename Body>
 __device__ __forceinline__ void sell_stream_rows(const SellView A, const double *__restrict__ x,
-						 const StreamConfig cfg, unsigned char *smem, Body body)
+						 const StreamConfig cfg, unsigned char *smem, Gate gate, Body body)
 {
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t total_warps = gridDim.x * kStreamWarps;
@@ -162,6 +171,14 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				issue(st, (uint32_t)s);
 		}
 	__syncwarp();
+	pdl_wait();
+	if (!gate()) {
+		// a CTA must not exit with bulk copies still landing in its shared memory
+		for (uint32_t st = 0; st < cfg.stages; st++)
+			if ((uint64_t)first + (uint64_t)st * total_warps < A.n_slices)
+				mbar_wait(bars + st, 0);
+		return;
+	}
 
 	uint32_t n = 0;
 	for (uint64_t s64 = first; s64 < A.n_slices; s64 += total_warps, n++) {
@@ -174,25 +191,46 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		const double *sval = reinterpret_cast<const double *>(stage) + lane;
 		const uint32_t row = s * kSliceRows + lane;
 		const uint32_t safe = min(row, A.N - 1);
-		double acc = 0.0, diag = 0.0;
+		double acc = 0.0, diag = 0.0, x_row = 0.0;
+		bool have_row = false;
 		if (!BLOCKED) {
 			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + lane;
-			for (uint32_t j0 = 0; j0 < width; j0 += kGatherBatch) {
+			uint32_t j0 = 0;
+			// full batches: column ids, then ALL gathers, then (behind a warp barrier that
+			// keeps the shared-memory value loads and hence the math from creeping up
+			// between the gathers) the accumulation
+			for (; j0 + kGatherBatch <= width; j0 += kGatherBatch) {
 				uint32_t cj[kGatherBatch];
 				double xj[kGatherBatch];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					cj[u] = (j0 + u < width) ? scol[(j0 + u) * kSliceRows] : kPadCol;
+					cj[u] = scol[(j0 + u) * kSliceRows];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
 					xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? safe : cj[u]));
+				__syncwarp();
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++) {
-					const double v = (j0 + u < width) ? sval[(j0 + u) * kSliceRows] : 0.0;
+					const double v = sval[(j0 + u) * kSliceRows];
 					const double t = __dmul_rn(v, xj[u]);
 					acc = (cj[u] == kPadCol) ? acc : __dadd_rn(acc, t);
-					if (WANT_DIAG && cj[u] == row)
+					if (cj[u] == row) {
 						diag = v;
+						x_row = xj[u];
+						have_row = true;
+					}
+				}
+			}
+			for (; j0 < width; j0++) {
+				const uint32_t cj = scol[j0 * kSliceRows];
+				const double v = sval[j0 * kSliceRows];
+				const double xj = ld_gather_f64(x + (cj == kPadCol ? safe : cj));
+				const double t = __dmul_rn(v, xj);
+				acc = (cj == kPadCol) ? acc : __dadd_rn(acc, t);
+				if (cj == row) {
+					diag = v;
+					x_row = xj;
+					have_row = true;
 				}
 			}
 		} else {
@@ -200,30 +238,52 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + (lane >> 1);
 			const uint32_t nblk = width >> 1;
 			const uint32_t safe_node = safe >> 1;
-			for (uint32_t b0 = 0; b0 < nblk; b0 += kGatherBatch) {
+			const uint32_t my_node = row >> 1;
+			uint32_t b0 = 0;
+			for (; b0 + kGatherBatch <= nblk; b0 += kGatherBatch) {
 				uint32_t cb[kGatherBatch];
 				double2 xb[kGatherBatch];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					cb[u] = (b0 + u < nblk) ? scol[(b0 + u) * 16u] : kPadCol;
+					cb[u] = scol[(b0 + u) * 16u];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
 					xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? safe_node : cb[u]));
+				__syncwarp();
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++) {
-					const bool in = b0 + u < nblk;
-					const double v0 = in ? sval[(2 * (b0 + u)) * kSliceRows] : 0.0;
-					const double v1 = in ? sval[(2 * (b0 + u) + 1) * kSliceRows] : 0.0;
+					const double v0 = sval[(2 * (b0 + u)) * kSliceRows];
+					const double v1 = sval[(2 * (b0 + u) + 1) * kSliceRows];
 					const bool pad = cb[u] == kPadCol;
 					const double t0 = __dmul_rn(v0, xb[u].x);
 					acc = pad ? acc : __dadd_rn(acc, t0);
 					const double t1 = __dmul_rn(v1, xb[u].y);
 					acc = pad ? acc : __dadd_rn(acc, t1);
-					if (WANT_DIAG && !pad && cb[u] == (row >> 1))
+					if (cb[u] == my_node) {
 						diag = (row & 1) ? v1 : v0;
+						x_row = (row & 1) ? xb[u].y : xb[u].x;
+						have_row = true;
+					}
+				}
+			}
+			for (; b0 < nblk; b0++) {
+				const uint32_t cb = scol[b0 * 16u];
+				const double v0 = sval[(2 * b0) * kSliceRows], v1 = sval[(2 * b0 + 1) * kSliceRows];
+				const double2 xb = ld_gather_f64x2(x + 2 * (size_t)(cb == kPadCol ? safe_node : cb));
+				const bool pad = cb == kPadCol;
+				const double t0 = __dmul_rn(v0, xb.x);
+				acc = pad ? acc : __dadd_rn(acc, t0);
+				const double t1 = __dmul_rn(v1, xb.y);
+				acc = pad ? acc : __dadd_rn(acc, t1);
+				if (cb == my_node) {
+					diag = (row & 1) ? v1 : v0;
+					x_row = (row & 1) ? xb.y : xb.x;
+					have_row = true;
 				}
 			}
 		}
+		if (!have_row && row < A.N)
+			x_row = __ldg(x + row);   // row without a stored diagonal
 		// every lane is done with the stage: hand it back to the producer
 		__syncwarp();
 		if (lane == 0) {
@@ -233,7 +293,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				issue(st, (uint32_t)next);
 			}
 		}
-		body(row, acc, diag);
+		body(row, acc, diag, x_row);
 	}
 }
 

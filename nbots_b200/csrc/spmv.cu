@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kBlock, 2)
 spmv_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ x, double *__restrict__ y)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	sell_stream_rows<BLOCKED, false>(A, x, cfg, smem, [&](uint32_t row, double acc, double) {
+	sell_stream_rows<BLOCKED, false>(A, x, cfg, smem, [] { return true; }, [&](uint32_t row, double acc, double, double) {
 		if (row < A.N)
 			y[row] = acc;
 	});
