@@ -118,10 +118,11 @@ def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
-        import torch
+        # torch.distributed is the rendezvous only (exchange of halo lists and CUDA IPC handles, barriers,
+        # max-over-ranks of the timings): gloo is enough -- the solver's own traffic goes over NVLink
+        # as peer stores issued by its kernels, not through a collective library.
         import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+        dist.init_process_group("gloo")
         return rank, world, dist
     return rank, world, None
 

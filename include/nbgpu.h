@@ -335,6 +335,69 @@ int nbgpu_fem_static_elasticity2d(const nbgpu_mesh_desc_t *mesh,
 				  double solver_tol, double *displacement,
 				  double *strain, nbgpu_fem_report_t *report);
 
+/* -------------------------------------------------------- multi-GPU -- */
+/* Row-partitioned solves over several GPUs of one node, one process per GPU
+ * (SURVEY.md §8e).  The reference has no distributed mode; these entry points
+ * mirror the single-GPU ones with a partition plan added.  Halo values and
+ * dot-product partials travel as NVLink peer stores into CUDA-IPC windows; no
+ * collective library is called inside the iteration. */
+
+typedef struct nbgpu_dist_s nbgpu_dist_t;             /* this rank's window + peers */
+typedef struct nbgpu_dist_plan_s nbgpu_dist_plan_t;   /* halo / send lists of one matrix */
+
+#define NBGPU_IPC_HANDLE_BYTES 64
+
+/* a rank-local block of the matrix: N_rows owned rows, columns numbered
+ * "owned, then halo" (see nbgpu_dist_plan_local_cols), entries of a row left in
+ * ascending GLOBAL column order */
+int nbgpu_matrix_create_local(uint32_t N_rows, uint32_t N_cols,
+			      const uint32_t *rows_size,
+			      const uint32_t *cols_local, const double *vals,
+			      nbgpu_matrix_t **out);
+
+/* Host logic (no device needed): rank `rank` of `world` owns global rows
+ * [row_starts[rank], row_starts[rank+1]); rows_size / cols_global describe those
+ * rows in CSR form with GLOBAL column ids. */
+int nbgpu_dist_plan_create(int rank, int world, const uint32_t *row_starts,
+			   const uint32_t *rows_size, const uint32_t *cols_global,
+			   nbgpu_dist_plan_t **out);
+int nbgpu_dist_plan_destroy(nbgpu_dist_plan_t *plan);
+/* recv_counts[world]: how many halo values come from each rank */
+int nbgpu_dist_plan_info(const nbgpu_dist_plan_t *plan, uint32_t *N_loc,
+			 uint32_t *n_halo, uint64_t *nnz, uint32_t *recv_counts);
+/* the halo columns (global row ids, ascending => grouped by owner) */
+int nbgpu_dist_plan_halo_ids(const nbgpu_dist_plan_t *plan, uint32_t *halo_global);
+int nbgpu_dist_plan_local_cols(const nbgpu_dist_plan_t *plan, uint32_t *cols_local);
+/* what the other ranks need from me (the transpose of their halo lists, which the
+ * processes exchange by any means): send_global grouped by destination in the
+ * order of the destination's halo list; dst_offsets[d] = position of my block in
+ * rank d's halo list */
+int nbgpu_dist_plan_set_sends(nbgpu_dist_plan_t *plan, const uint32_t *send_counts,
+			      const uint32_t *send_global, const uint32_t *dst_offsets);
+
+/* ext_len >= N_loc + n_halo.  Writes this rank's 64-byte CUDA IPC handle. */
+int nbgpu_dist_create(int rank, int world, size_t ext_len, void *ipc_handle_out,
+		      nbgpu_dist_t **out);
+/* all_handles: world x 64 bytes in rank order; all_ext_len: every rank's ext_len */
+int nbgpu_dist_connect(nbgpu_dist_t *dist, const void *all_handles,
+		       const uint64_t *all_ext_len);
+int nbgpu_dist_destroy(nbgpu_dist_t *dist);
+int nbgpu_dist_error(nbgpu_dist_t *dist);
+
+/* Collective over all ranks (every rank calls with its own block).  b, x: this
+ * rank's rows; tolerance is the absolute bound on the GLOBAL residual norm, as in
+ * the single-GPU call; every rank returns the same status / iteration count. */
+int nbgpu_dist_pcg_jacobi(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
+			  const nbgpu_matrix_t *A_local, const double *d_b,
+			  double *d_x, uint32_t max_iter, double tolerance,
+			  uint32_t *niter_performed, double *tolerance_reached);
+int nbgpu_dist_cg(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
+		  const nbgpu_matrix_t *A_local, const double *d_b, double *d_x,
+		  uint32_t max_iter, double tolerance, uint32_t *niter_performed,
+		  double *tolerance_reached);
+int nbgpu_dist_spmv(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
+		    const nbgpu_matrix_t *A_local, const double *d_in, double *d_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,22 @@ SIGNATURES = {
     "nbgpu_apply_dirichlet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p, f64p]),
     "nbgpu_compute_strain": (C.c_int, [C.c_void_p, C.POINTER(ElemTables), C.c_void_p, C.c_void_p]),
     "nbgpu_stress_from_strain": (C.c_int, [C.c_uint32, C.c_uint32, f64p, f64p, u8p, C.c_void_p, C.c_void_p]),
+    "nbgpu_matrix_create_local": (C.c_int, [C.c_uint32, C.c_uint32, u32p, u32p, f64p, vpp]),
+    "nbgpu_dist_plan_create": (C.c_int, [C.c_int, C.c_int, u32p, u32p, u32p, vpp]),
+    "nbgpu_dist_plan_destroy": (C.c_int, [C.c_void_p]),
+    "nbgpu_dist_plan_info": (C.c_int, [C.c_void_p, u32p, u32p, u64p, u32p]),
+    "nbgpu_dist_plan_halo_ids": (C.c_int, [C.c_void_p, u32p]),
+    "nbgpu_dist_plan_local_cols": (C.c_int, [C.c_void_p, u32p]),
+    "nbgpu_dist_plan_set_sends": (C.c_int, [C.c_void_p, u32p, u32p, u32p]),
+    "nbgpu_dist_create": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, vpp]),
+    "nbgpu_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
+    "nbgpu_dist_destroy": (C.c_int, [C.c_void_p]),
+    "nbgpu_dist_error": (C.c_int, [C.c_void_p]),
+    "nbgpu_dist_pcg_jacobi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                        C.c_double, u32p, f64p]),
+    "nbgpu_dist_cg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
+                                u32p, f64p]),
+    "nbgpu_dist_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -18,7 +18,7 @@ constexpr size_t kStageBytes = size_t(32) << 20;   // per pinned staging buffer
 // are not strictly ascending or out of range (the reference's invariant after
 // nb_qsort, sparse.c:55).
 __global__ void __launch_bounds__(kBlock)
-csr_to_sell_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
+csr_to_sell_kernel(uint32_t N, uint32_t n_cols, bool sorted, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
 		   const uint32_t *__restrict__ csr_col, const double *__restrict__ csr_val,
 		   const uint32_t *__restrict__ slice_off, uint32_t *__restrict__ sell_col,
 		   double *__restrict__ sell_val, int *bad)
@@ -40,7 +40,7 @@ csr_to_sell_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ r
 			if (j < len) {
 				if (sell_col) {
 					uint32_t c = csr_col[base + j];
-					if (c >= N || (j > 0 && c <= prev))
+					if (c >= n_cols || (sorted && j > 0 && c <= prev))
 						*bad = 1;
 					prev = c;
 					sell_col[idx] = c;
@@ -238,6 +238,8 @@ struct DeviceTemp {
 int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
 {
 	A->N = N;
+	if (A->n_cols == 0)
+		A->n_cols = N;
 	A->h_rows_size.assign(rows_size, rows_size + N);
 	A->h_row_ptr.resize((size_t)N + 1);
 	A->h_row_ptr[0] = 0;
@@ -294,7 +296,7 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 	NB_CUDA(cudaStreamSynchronize(c.copy_stream));   // staged uploads have landed
 	if (A->n_slices) {
 		csr_to_sell_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
-			A->N, A->n_slices, (const uint64_t *)rp.p, d_cols, d_vals, A->d_slice_off,
+			A->N, A->n_cols, !A->local_block, A->n_slices, (const uint64_t *)rp.p, d_cols, d_vals, A->d_slice_off,
 			d_cols ? A->d_col : nullptr, A->d_val, (int *)bad.p);
 		NB_LAUNCHED();
 	}
@@ -375,6 +377,34 @@ int nbgpu_matrix_create_from_csr(uint32_t N, const uint32_t *rows_size, const ui
 		st = dv.alloc(A->nnz * sizeof(double));
 	if (st == NBGPU_OK)
 		st = upload_flat<uint32_t>((uint32_t *)dc.p, cols, A->nnz);
+	if (st == NBGPU_OK && vals)
+		st = upload_flat<double>((double *)dv.p, vals, A->nnz);
+	if (st == NBGPU_OK)
+		st = convert_in(A, (const uint32_t *)dc.p, vals ? (const double *)dv.p : nullptr);
+	if (st != NBGPU_OK) {
+		nbgpu_matrix_destroy(A);
+		return st;
+	}
+	*out = A;
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_create_local(uint32_t N_rows, uint32_t N_cols, const uint32_t *rows_size,
+			      const uint32_t *cols_local, const double *vals, nbgpu_matrix_t **out)
+{
+	NB_INIT();
+	NB_ARG(out != nullptr && N_cols >= N_rows && (N_rows == 0 || (rows_size != nullptr && cols_local != nullptr)));
+	nbgpu_matrix_t *A = new nbgpu_matrix_t();
+	A->n_cols = N_cols;
+	A->local_block = true;
+	int st = build_layout(A, N_rows, rows_size);
+	DeviceTemp dc, dv;
+	if (st == NBGPU_OK)
+		st = dc.alloc(A->nnz * sizeof(uint32_t));
+	if (st == NBGPU_OK && vals)
+		st = dv.alloc(A->nnz * sizeof(double));
+	if (st == NBGPU_OK)
+		st = upload_flat<uint32_t>((uint32_t *)dc.p, cols_local, A->nnz);
 	if (st == NBGPU_OK && vals)
 		st = upload_flat<double>((double *)dv.p, vals, A->nnz);
 	if (st == NBGPU_OK)

@@ -15,7 +15,10 @@
 #include "common.cuh"
 
 struct nbgpu_matrix_s {
-	uint32_t N = 0;
+	uint32_t N = 0;                       // rows
+	uint32_t n_cols = 0;                  // column space (== N except for a rank-local block, which
+					      // appends its halo columns after the owned ones)
+	bool local_block = false;             // columns are local ids in ascending GLOBAL order: not sorted
 	uint64_t nnz = 0;
 	uint32_t n_slices = 0;
 	uint64_t stored = 0;                  // padded entry count = 32 * slice_off[n_slices]

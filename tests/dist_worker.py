@@ -1,0 +1,173 @@
+"""Worker of the multi-rank tests (launched once per rank).
+
+  mode cpu : gloo, no GPU -- the product's partition plan + list exchange, with the local arithmetic done by the
+             oracle (numpy / oracle.port) and the halo / reductions moved over gloo.
+  mode gpu : one rank per GPU (or all ranks on GPU 0 when fewer are visible) -- nbgpu_dist_* end to end.
+Rank 0 prints DIST_OK on success."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from nbots_b200 import multigpu  # noqa: E402
+from oracle import port  # noqa: E402
+from util import golden, rel_l2  # noqa: E402
+
+
+def gather_obj_fn(world):
+    def f(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    return f
+
+
+def split_rows(g, world):
+    """Row blocks of the golden quad cantilever cut between grid lines (64 x 16 elements -> 65 x 17 nodes)."""
+    NX, NY = 65, 17
+    lines = multigpu.slab_lines(NY, world)
+    return np.array([2 * NX * j for j in lines], dtype=np.uint32)
+
+
+def run_cpu(rank, world):
+    g = golden("quad_cantilever_64x16")
+    rs, cols, vals, b = g["rows_size"], g["cols"], g["K_post"], g["F_post"]
+    rp = port.row_ptr_of(rs).astype(np.int64)
+    row_starts = split_rows(g, world)
+    r0, r1 = int(row_starts[rank]), int(row_starts[rank + 1])
+    gather = gather_obj_fn(world)
+    dc = multigpu.DistContext(rank, world, row_starts, rs[r0:r1], cols[rp[r0]:rp[r1]], None, gather)
+    # plan invariants
+    assert dc.N_loc == r1 - r0 and dc.n_halo == dc.recv_counts.sum()
+    assert np.all(np.diff(dc.halo_global.astype(np.int64)) > 0)
+    assert not np.any((dc.halo_global >= r0) & (dc.halo_global < r1))
+    assert np.array_equal(np.sort(np.unique(cols[rp[r0]:rp[r1]][(cols[rp[r0]:rp[r1]] < r0) | (cols[rp[r0]:rp[r1]] >= r1)])),
+                          dc.halo_global)
+    A_loc = port.Csr(rs[r0:r1], dc.cols_local, vals[rp[r0]:rp[r1]])       # local ids, entry order untouched
+
+    def exchange(v_loc):
+        """halo of a distributed vector: what nbots_b200/csrc/dist.cu does with peer stores, here over gloo"""
+        sends = []
+        off = 0
+        for d in range(world):
+            cnt = int(dc.send_counts[d])
+            sends.append(v_loc[dc.send_global[off:off + cnt] - r0].copy())
+            off += cnt
+        everyone = gather(sends)
+        ext = np.zeros(dc.N_loc + dc.n_halo)
+        ext[:dc.N_loc] = v_loc
+        pos = dc.N_loc
+        for src in range(world):
+            chunk = everyone[src][rank]
+            assert chunk.size == dc.recv_counts[src]
+            ext[pos:pos + chunk.size] = chunk
+            pos += chunk.size
+        return ext
+
+    def allsum(*vals_):
+        t = torch.tensor(list(vals_), dtype=torch.float64)
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return [float(sum(p[i].item() for p in parts)) for i in range(len(vals_))]     # rank order, like dist.cu
+
+    # distributed SpMV == the serial oracle's rows, bit for bit
+    x = g["x"]
+    y_loc = A_loc.spmv(exchange(x[r0:r1]))
+    assert np.array_equal(y_loc, g["spmv_x"][r0:r1])
+
+    # distributed Jacobi-PCG (cg_precond_jacobi.c:13-90) with the plan's halo exchange
+    tol = float(g["tol"])
+    xl = np.zeros(dc.N_loc)
+    gl = A_loc.spmv(exchange(xl)) - b[r0:r1]
+    diag = np.array([vals[rp[r0 + i]:rp[r0 + i + 1]][cols[rp[r0 + i]:rp[r0 + i + 1]] == r0 + i][0]
+                     for i in range(dc.N_loc)])
+    ql = gl / diag
+    pl = -ql
+    gg, gq = allsum(gl @ gl, gl @ ql)
+    gg_test, k = gg, 0
+    while gg_test > tol * tol and k < rs.size:
+        wl = A_loc.spmv(exchange(pl))
+        pw, = allsum(pl @ wl)
+        gg_test = gg
+        alpha = gq / pw
+        xl += alpha * pl
+        gl += alpha * wl
+        ql = gl / diag
+        gg, gq_new = allsum(gl @ gl, gl @ ql)
+        pl = -ql + (gq_new / gq) * pl
+        gq = gq_new
+        k += 1
+    xs = gather(xl)
+    if rank == 0:
+        xg = np.concatenate(xs)
+        assert abs(k - int(g["pcg_iters"])) <= max(1, int(0.02 * int(g["pcg_iters"]))), (k, int(g["pcg_iters"]))
+        assert rel_l2(xg, g["x"]) <= 1e-10
+        print("DIST_OK cpu", k)
+
+
+def run_gpu(rank, world):
+    from nbots_b200 import api, capi
+    n_dev = torch.cuda.device_count()
+    L = capi.lib()
+    capi.check(L.nbgpu_init(rank % n_dev))
+    gather = gather_obj_fn(world)
+    g = golden("quad_cantilever_64x16")
+    prob = multigpu.SlabProblem(64, 16, 4.0, 1.0, rank, world)
+    rp = port.row_ptr_of(g["rows_size"]).astype(np.int64)
+    r0, r1 = int(prob.row_starts[rank]), int(prob.row_starts[rank + 1])
+    # this rank's rows of the global system, bit for bit the reference's
+    assert np.array_equal(prob.rows_size, g["rows_size"][r0:r1])
+    assert np.array_equal(prob.cols_global, g["cols"][rp[r0]:rp[r1]])
+    assert np.array_equal(prob.vals, g["K_post"][rp[r0]:rp[r1]])
+    assert np.array_equal(prob.b, g["F_post"][r0:r1])
+    dc = multigpu.DistContext(rank, world, prob.row_starts, prob.rows_size, prob.cols_global, prob.vals, gather)
+    d_b = api.DeviceBuffer.from_host(prob.b)
+    # distributed SpMV: bit-exact rows of the serial product
+    d_in = api.DeviceBuffer.from_host(g["x"][r0:r1])
+    d_out = api.DeviceBuffer.zeros(prob.N_loc)
+    for _ in range(3):
+        dc.spmv(d_in, d_out)
+    assert np.array_equal(d_out.to_host(), g["spmv_x"][r0:r1])
+    tol = float(g["tol"])
+    results = []
+    for rep in range(2):
+        d_x = api.DeviceBuffer.zeros(prob.N_loc)
+        st, it, res = dc.pcg_jacobi(d_b, d_x, prob.N_global, tol)
+        results.append((st, it, res, d_x.to_host()))
+    assert results[0][1] == results[1][1] and np.array_equal(results[0][3], results[1][3])   # reproducible
+    st, it, res, xl = results[0]
+    st_c, it_c, res_c = dc.cg(d_b, api.DeviceBuffer.zeros(prob.N_loc), prob.N_global, tol)
+    # max_iter exit on every rank at the same count
+    d_x = api.DeviceBuffer.zeros(prob.N_loc)
+    st_cap, it_cap, _ = dc.pcg_jacobi(d_b, d_x, 17, 0.0)
+    everyone = gather((st, it, res, xl, st_cap, it_cap, st_c, it_c))
+    assert len({(e[0], e[1], e[2]) for e in everyone}) == 1, "ranks disagree on status / iterations / residual"
+    if rank == 0:
+        xg = np.concatenate([e[3] for e in everyone])
+        assert st == 0 and abs(it - int(g["pcg_iters"])) <= max(1, int(0.02 * int(g["pcg_iters"])))
+        assert rel_l2(xg, g["x"]) <= 1e-10
+        assert (st_cap, it_cap) == (1, 17)
+        assert st_c == int(g["cg_status"]) and abs(it_c - int(g["cg_iters"])) <= max(1, int(0.02 * int(g["cg_iters"])))
+        print("DIST_OK gpu", it, api.launch_count())
+    dc.close()
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    try:
+        (run_cpu if mode == "cpu" else run_gpu)(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

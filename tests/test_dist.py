@@ -1,0 +1,33 @@
+"""Multi-rank path: world_size-2/3 gloo runs on CPU for the host-side logic (partition plan, halo/send lists,
+exchange protocol), and the real thing on GPUs (`-m gpu`)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "dist_worker.py")
+
+
+def launch(mode, world, port, timeout=600, extra_env=None):
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, mode]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partition_plan_and_exchange_on_cpu(world):
+    out = launch("cpu", world, 29600 + world)
+    assert out.returncode == 0 and "DIST_OK cpu" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2])
+def test_distributed_solve_on_gpus(nbgpu_lib, world):
+    """One rank per GPU when the box has several; on a single-GPU box both ranks share GPU 0 (CUDA IPC works
+    within one device; the kernels of the two processes are time-sliced, so this only checks correctness)."""
+    out = launch("gpu", world, 29700 + world, timeout=900, extra_env={"NBGPU_DIST_TIMEOUT_MS": "60000"})
+    assert out.returncode == 0 and "DIST_OK gpu" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
