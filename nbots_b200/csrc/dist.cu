@@ -49,10 +49,10 @@ struct DistControl {
 	unsigned long long halo_seq[kMaxRanks];   // p halo pushed by rank src
 	unsigned long long xh_seq[kMaxRanks];     // generic vector halo (x at init, SpMV input)
 	unsigned long long xh_ack[kMaxRanks];     // ... consumed by rank dst (flow control for SpMV)
-	unsigned long long pw_seq[kMaxRanks];
-	unsigned long long gq_seq[kMaxRanks];
-	double pw_val[kMaxRanks];
-	double gq_val[kMaxRanks][2];              // (g.g, g.q) partials
+	// Reduction partials travel as self-validating 16-byte messages {value bits, sequence}: one
+	// NVLink store per message, no fence on the sender, the receiver polls the pair.
+	ulonglong2 pw_msg[kMaxRanks];             // p.w partial of rank src
+	ulonglong2 gq_msg[kMaxRanks][2];          // (g.g, g.q) partials of rank src
 	int error;
 };
 
@@ -89,6 +89,18 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 {
 	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_msg(ulonglong2 *p, double v, unsigned long long seq)
+{
+	asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((unsigned long long)__double_as_longlong(v)),
+		     "l"(seq)
+		     : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_msg(const ulonglong2 *p)
+{
+	ulonglong2 m;
+	asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(m.x), "=l"(m.y) : "l"(p) : "memory");
+	return m;
+}
 __device__ __forceinline__ unsigned long long global_ns()
 {
 	unsigned long long t;
@@ -116,23 +128,63 @@ __device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigne
 	}
 }
 
-// CTA-wide and CTA-uniform: false if the solve is over (done / error), else thread r
-// waits for rank r's flag; false again if any wait failed
-template <typename FlagOf>
-__device__ __forceinline__ bool cta_wait_all(int world, FlagOf flag_of, unsigned long long seq, DistControl *mine,
-					     unsigned long long timeout_ns, const int32_t *done)
+// one thread waits for the message with sequence `seq`; the value comes back in *v
+__device__ __forceinline__ bool wait_msg(const ulonglong2 *slot, unsigned long long seq, double *v, DistControl *mine,
+					 unsigned long long timeout_ns)
+{
+	unsigned long long t0 = 0;
+	for (unsigned int spin = 0;; spin++) {
+		const ulonglong2 m = ld_msg(slot);
+		if (m.y == seq) {
+			*v = __longlong_as_double((long long)m.x);
+			return true;
+		}
+		if (spin < 64)
+			continue;   // the common case: the message is at most a few microseconds away
+		if (t0 == 0)
+			t0 = global_ns();
+		if (*(volatile int *)&mine->error)
+			return false;
+		if (global_ns() - t0 > timeout_ns) {
+			*(volatile int *)&mine->error = 1;
+			return false;
+		}
+		__nanosleep(32);
+	}
+}
+
+// CTA-wide, CTA-uniform gather of NV-value messages from every rank, summed in rank order.
+// false if the solve is over (done / error) or a wait failed.
+template <int NV, typename SlotOf>
+__device__ __forceinline__ bool cta_reduce_msgs(int world, SlotOf slot_of, unsigned long long seq, DistControl *mine,
+						unsigned long long timeout_ns, const int32_t *done, double (&tot)[NV])
 {
 	__shared__ int s_ok;
+	__shared__ double s_val[NV][kMaxRanks];
 	if (threadIdx.x == 0)
 		s_ok = !(done && *(volatile const int32_t *)done) && !*(volatile int *)&mine->error;
 	__syncthreads();
 	if (!s_ok)
 		return false;
 	__syncthreads();
-	if ((int)threadIdx.x < world && !wait_seq(flag_of(threadIdx.x), seq, mine, timeout_ns))
-		s_ok = 0;
+	if ((int)threadIdx.x < world * NV) {
+		const int r = threadIdx.x / NV, c = threadIdx.x % NV;
+		double v = 0.0;
+		if (!wait_msg(slot_of(r, c), seq, &v, mine, timeout_ns))
+			s_ok = 0;
+		s_val[c][r] = v;
+	}
 	__syncthreads();
-	return s_ok != 0;
+	if (!s_ok)
+		return false;
+#pragma unroll
+	for (int c = 0; c < NV; c++) {
+		double t = 0.0;
+		for (int r = 0; r < world; r++)
+			t += s_val[c][r];
+		tot[c] = t;
+	}
+	return true;
 }
 
 // ---- halo push: one CTA per destination ----------------------------------------
@@ -185,20 +237,14 @@ halo_push_kernel(PeerTable T, const uint32_t *__restrict__ send_idx, const doubl
 __device__ __forceinline__ void post_pw(const PeerTable &T, double v, unsigned long long seq)
 {
 	if ((int)threadIdx.x < T.world) {
-		DistControl *peer = T.ctrl[threadIdx.x];
-		peer->pw_val[T.rank] = v;
-		__threadfence_system();
-		st_release_sys(&peer->pw_seq[T.rank], seq);
+		st_msg(&T.ctrl[threadIdx.x]->pw_msg[T.rank], v, seq);
 	}
 }
 __device__ __forceinline__ void post_gq(const PeerTable &T, double gg, double gq, unsigned long long seq)
 {
 	if ((int)threadIdx.x < T.world) {
-		DistControl *peer = T.ctrl[threadIdx.x];
-		peer->gq_val[T.rank][0] = gg;
-		peer->gq_val[T.rank][1] = gq;
-		__threadfence_system();
-		st_release_sys(&peer->gq_seq[T.rank], seq);
+		st_msg(&T.ctrl[threadIdx.x]->gq_msg[T.rank][0], gg, seq);
+		st_msg(&T.ctrl[threadIdx.x]->gq_msg[T.rank][1], gq, seq);
 	}
 }
 
@@ -245,7 +291,7 @@ dist_init_kernel(SellView A, StreamConfig cfg, PeerTable T, unsigned long long s
 	double dots[2] = {0.0, 0.0};
 	bool ok = true;
 	sell_stream_rows<BLOCKED, JACOBI>(
-		A, x_ext, cfg, smem,
+		A, x_ext, cfg, smem, [] { return true; },
 		[&] {
 			ok = warp_wait_halo(T, 1, seq);
 			return ok;
@@ -284,16 +330,13 @@ __global__ void dist_init_reduce_kernel(PeerTable T, unsigned long long seq, Dis
 	pdl_wait();
 	pdl_launch_dependents();
 	DistControl *mine = T.ctrl[T.rank];
-	if (!cta_wait_all(T.world, [&](int r) { return &mine->gq_seq[r]; }, seq, mine, T.timeout_ns, nullptr))
+	double tot[2];
+	if (!cta_reduce_msgs<2>(T.world, [&](int r, int c) { return &mine->gq_msg[r][c]; }, seq, mine, T.timeout_ns,
+				nullptr, tot))
 		return;
 	if (threadIdx.x == 0) {
-		double gg = 0.0, gq = 0.0;
-		for (int r = 0; r < T.world; r++) {
-			gg += mine->gq_val[r][0];
-			gq += mine->gq_val[r][1];
-		}
-		st->gg[0] = gg;
-		st->gq[0] = gq;
+		st->gg[0] = tot[0];
+		st->gq[0] = tot[1];
 	}
 }
 
@@ -310,10 +353,9 @@ dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned
 		A, p_ext, cfg, smem,
 		[&] {
 			active = iteration_gate(k, st) && !*(volatile int *)&T.ctrl[T.rank]->error;
-			if (active)
-				active = warp_wait_halo(T, 0, base + k + 1);
 			return active;
 		},
+		[&] { return warp_wait_halo(T, 0, base + k + 1); },   // only the slices that read halo columns wait
 		[&](uint32_t row, double acc, double, double p_row) {
 			if (row < A.N) {
 				w[row] = acc;
@@ -340,26 +382,43 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		   const double *__restrict__ w, const double *__restrict__ diag, double *__restrict__ x,
 		   double *__restrict__ g, double *__restrict__ q, double *partials, DistState *st)
 {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t base_i = blockIdx.x * blockDim.x + threadIdx.x;
+	double p0 = 0, x0 = 0, g0 = 0, d0 = 1, p1 = 0, x1 = 0, g1 = 0, d1 = 1;
+	if (base_i < N) {
+		const uint32_t j1 = base_i + stride < N ? base_i + stride : base_i;
+		p0 = p[base_i]; x0 = x[base_i]; g0 = g[base_i];
+		p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+		if (JACOBI) {
+			d0 = diag[base_i];
+			d1 = diag[j1];
+		}
+	}
 	pdl_wait();
 	pdl_launch_dependents();
 	DistControl *mine = T.ctrl[T.rank];
-	if (!cta_wait_all(T.world, [&](int r) { return &mine->pw_seq[r]; }, base + k + 1, mine, T.timeout_ns, &st->done))
+	double pw_tot[1];
+	if (!cta_reduce_msgs<1>(T.world, [&](int r, int) { return &mine->pw_msg[r]; }, base + k + 1, mine, T.timeout_ns,
+				&st->done, pw_tot))
 		return;
-	double pw = 0.0;
-	for (int r = 0; r < T.world; r++)
-		pw += mine->pw_val[r];
+	const double pw = pw_tot[0];
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		st->pw = pw;
 	const double alpha = __ddiv_rn(st->gq[k & 1], pw);
 	double dots[2] = {0.0, 0.0};
-	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < N; i0 += 2 * stride) {
+	for (uint32_t i0 = base_i; i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
-		const double p0 = p[i0], x0 = x[i0], g0 = g[i0], w0 = w[i0];
-		const double p1 = p[j1], x1 = x[j1], g1 = g[j1], w1 = w[j1];
-		const double d0 = JACOBI ? diag[i0] : 1.0, d1 = JACOBI ? diag[j1] : 1.0;
+		if (i0 != base_i) {
+			p0 = p[i0]; x0 = x[i0]; g0 = g[i0];
+			p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+			if (JACOBI) {
+				d0 = diag[i0];
+				d1 = diag[j1];
+			}
+		}
+		const double w0 = w[i0], w1 = w[j1];
 		const double gn0 = __dadd_rn(g0, __dmul_rn(alpha, w0));
 		const double gn1 = __dadd_rn(g1, __dmul_rn(alpha, w1));
 		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
@@ -386,21 +445,22 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		post_gq(T, tot[0], JACOBI ? tot[1] : tot[0], base + k + 2);
 }
 
-// ---- K3: waits for all (g.g, g.q), p = -q + beta p ---------------------------------
+// ---- K3: waits for all (g.g, g.q), p = -q + beta p, pushes the boundary of p --------
+// The CTA that finishes last (ticket) sends this rank's boundary entries of the new p
+// into the neighbours' halo tails and raises their flags: the exchange is part of the
+// kernel that produces the data, no separate launch.
 __global__ void __launch_bounds__(kBlock)
 dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, const double *__restrict__ q,
-		double *__restrict__ p, DistState *st)
+		double *__restrict__ p, const uint32_t *__restrict__ send_idx, DistState *st)
 {
 	pdl_wait();
 	pdl_launch_dependents();
 	DistControl *mine = T.ctrl[T.rank];
-	if (!cta_wait_all(T.world, [&](int r) { return &mine->gq_seq[r]; }, base + k + 2, mine, T.timeout_ns, &st->done))
+	double tot[2];
+	if (!cta_reduce_msgs<2>(T.world, [&](int r, int c) { return &mine->gq_msg[r][c]; }, base + k + 2, mine,
+				T.timeout_ns, &st->done, tot))
 		return;
-	double gg = 0.0, gq = 0.0;
-	for (int r = 0; r < T.world; r++) {
-		gg += mine->gq_val[r][0];
-		gq += mine->gq_val[r][1];
-	}
+	const double gg = tot[0], gq = tot[1];
 	const double beta = __ddiv_rn(gq, st->gq[k & 1]);
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		st->gg[(k + 1) % 3u] = gg;
@@ -416,6 +476,28 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 		if (has1)
 			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
 	}
+	if (T.send_ptr[T.world] == 0)
+		return;
+	__shared__ bool last;
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0)
+		last = atomicInc(&st->ticket, gridDim.x - 1) == gridDim.x - 1;
+	__syncthreads();
+	if (!last)
+		return;
+	__threadfence();
+	const uint32_t total = T.send_ptr[T.world];
+	for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+		int d = 0;
+		while (j >= T.send_ptr[d + 1])
+			d++;
+		T.p_halo_dst[d][j - T.send_ptr[d]] = __ldcg(p + send_idx[j]);
+	}
+	__threadfence_system();
+	__syncthreads();
+	if ((int)threadIdx.x < T.world && T.send_ptr[threadIdx.x + 1] > T.send_ptr[threadIdx.x])
+		st_release_sys(&T.ctrl[threadIdx.x]->halo_seq[T.rank], base + k + 2);
 }
 
 // ---- distributed SpMV (config 3): y = A x with the halo of x exchanged first --------
@@ -426,7 +508,7 @@ dist_plain_spmv_kernel(SellView A, StreamConfig cfg, PeerTable T, unsigned long 
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	sell_stream_rows<BLOCKED, false>(
-		A, x_ext, cfg, smem, [&] { return warp_wait_halo(T, 1, seq); },
+		A, x_ext, cfg, smem, [] { return true; }, [&] { return warp_wait_halo(T, 1, seq); },
 		[&](uint32_t row, double acc, double, double) {
 			if (row < A.N)
 				y[row] = acc;
@@ -490,6 +572,10 @@ struct nbgpu_dist_plan_s {
 	std::vector<uint32_t> send_local;      // local row ids, grouped by destination
 	std::vector<uint32_t> dst_offset;      // [world] where my block starts in the destination's halo
 	uint32_t *d_send_idx = nullptr;
+	// SpMV visit order: start right after the last slice that reads halo columns, so that every
+	// halo-reading slice is visited at the end (visit index >= late_from) -- the halo wait of a
+	// kernel is then hidden behind the interior slices
+	uint32_t visit_shift = 0, late_from = 0;
 };
 
 struct nbgpu_dist_s {
@@ -563,6 +649,40 @@ int nbgpu_dist_plan_create(int rank, int world, const uint32_t *row_starts, cons
 			P->cols_local[k] = c - r0;
 		else
 			P->cols_local[k] = P->N_loc + (uint32_t)(std::lower_bound(halo.begin(), halo.end(), c) - halo.begin());
+	}
+	// largest (circular) run of slices that read no halo column = the interior
+	{
+		const uint32_t n_slices = (P->N_loc + kSliceRows - 1) / kSliceRows;
+		std::vector<uint8_t> reads_halo(n_slices, 0);
+		uint64_t k = 0;
+		for (uint32_t i = 0; i < P->N_loc; i++)
+			for (uint32_t j = 0; j < rows_size[i]; j++, k++)
+				if (P->cols_local[k] >= P->N_loc)
+					reads_halo[i / kSliceRows] = 1;
+		uint32_t best_start = 0, best_len = 0;
+		bool any = false;
+		for (uint32_t s0 = 0; s0 < n_slices; s0++) {
+			if (!reads_halo[s0])
+				continue;
+			any = true;
+			// run of clean slices that starts right after halo slice s0 (circularly)
+			uint32_t len = 0;
+			while (len < n_slices && !reads_halo[(s0 + 1 + len) % n_slices])
+				len++;
+			if (len > best_len || best_len == 0) {
+				if (len >= best_len) {
+					best_len = len;
+					best_start = (s0 + 1) % n_slices;
+				}
+			}
+		}
+		if (!any) {
+			P->visit_shift = 0;
+			P->late_from = 0xFFFFFFFFu;   // nothing to wait for
+		} else {
+			P->visit_shift = best_start;
+			P->late_from = best_len;
+		}
 	}
 	*out = P;
 	return NBGPU_OK;
@@ -778,7 +898,10 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 	NB_CUDA(cudaMemcpyAsync(xw, d_x, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 	NB_CUDA(cudaMemcpyAsync(x_ext, d_x, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 
-	const SellView V{N, A->n_slices, A->d_slice_off, A->d_val, A->blocked ? A->d_bcol : A->d_col};
+	SellView V;
+	V.N = N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
+	V.col = A->blocked ? A->d_bcol : A->d_col;
+	V.visit_shift = P->visit_shift; V.late_from = P->late_from;
 	StreamConfig scfg, icfg;
 	const void *sk = A->blocked ? (const void *)dist_spmv_kernel<true> : (const void *)dist_spmv_kernel<false>;
 	const void *ik = jacobi ? (A->blocked ? (const void *)dist_init_kernel<true, true>
@@ -844,10 +967,8 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 				e = launch(pdl, dist_update_kernel<false>, ugrid, kBlock, 0, k, N, T, base, (const double *)p, w,
 					   diag, xw, g, q, c.partials, st);
 			NB_CUDA(e);
-			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p, st));
-			if (n_dst)
-				NB_CUDA(launch(pdl, halo_push_kernel, n_dst, kBlock, 0, T, P->d_send_idx, (const double *)p, 0,
-					       base + k + 2, (const DistState *)st));
+			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p,
+				       (const uint32_t *)P->d_send_idx, st));
 		}
 		if (k == max_iter) {
 			if (A->blocked)
@@ -917,7 +1038,10 @@ int nbgpu_dist_spmv(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t 
 	Context &c = ctx();
 	PeerTable T;
 	NB_TRY(build_peer_table(D, P, &T));
-	const SellView V{A->N, A->n_slices, A->d_slice_off, A->d_val, A->blocked ? A->d_bcol : A->d_col};
+	SellView V;
+	V.N = A->N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
+	V.col = A->blocked ? A->d_bcol : A->d_col;
+	V.visit_shift = P->visit_shift; V.late_from = P->late_from;
 	StreamConfig cfg;
 	const void *kern = A->blocked ? (const void *)dist_plain_spmv_kernel<true>
 				      : (const void *)dist_plain_spmv_kernel<false>;

@@ -193,7 +193,7 @@ krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[2] = {0.0, 0.0};
 	sell_stream_rows<BLOCKED, JACOBI>(
-		A, x, cfg, smem, [] { return true; },
+		A, x, cfg, smem, [] { return true; }, [] { return true; },
 		[&](uint32_t row, double acc, double d, double) {
 			if (row < A.N)
 				init_row<JACOBI>(row, acc, d, b, g, p, q, diag, dots);
@@ -216,6 +216,7 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, const double
 			active = iteration_gate(k, st);
 			return active;
 		},
+		[] { return true; },
 		[&](uint32_t row, double acc, double, double p_row) {
 			if (row < A.N) {
 				w[row] = acc;
@@ -489,7 +490,9 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 				 : resident_grid(krylov_update_kernel<false>, vec_blocks);
 	const int dgrid = resident_grid(krylov_dir_kernel, vec_blocks);
 	// streamed (TMA) path: same kernels, matrix staged through shared memory
-	const SellView V{N, A->n_slices, A->d_slice_off, A->d_val, A->blocked ? A->d_bcol : A->d_col};
+	SellView V;
+	V.N = N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
+	V.col = A->blocked ? A->d_bcol : A->d_col;
 	StreamConfig scfg, icfg;
 	const void *sk = A->blocked ? (const void *)krylov_spmv_stream_kernel<true>
 				    : (const void *)krylov_spmv_stream_kernel<false>;

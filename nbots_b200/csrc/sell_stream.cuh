@@ -109,6 +109,11 @@ struct SellView {
 	const uint32_t *slice_off;
 	const double *val;
 	const uint32_t *col;    // per-entry column ids, or per-block node ids when BLOCKED
+	// Visit order (rank-local blocks of a partitioned matrix): the v-th slice visited is
+	// (v + visit_shift) mod n_slices, so that the slices whose rows read halo columns come last,
+	// and `late()` -- the wait for the halo -- is only called before visit index late_from.
+	uint32_t visit_shift = 0;
+	uint32_t late_from = 0xFFFFFFFFu;
 };
 
 // Runs `body(row, acc, diag, x_row)` for every row of the slices this warp owns
@@ -122,10 +127,13 @@ struct SellView {
 // BEFORE the programmatic-dependency wait: the bulk copies of this kernel
 // overlap the tail of the previous kernel in the stream.  `gate()` is evaluated
 // after the wait (it may read what the predecessor wrote); when it returns
-// false the warp only drains its in-flight copies and leaves.
-template <bool BLOCKED, bool WANT_DIAG, typename Gate, typename Body>
+// false the warp only drains its in-flight copies and leaves.  `late()` is
+// called once, before the first slice with visit index >= A.late_from (slices
+// that need data a peer GPU is still sending); false = give up likewise.
+template <bool BLOCKED, bool WANT_DIAG, typename Gate, typename Late, typename Body>
 __device__ __forceinline__ void sell_stream_rows(const SellView A, const double *__restrict__ x,
-						 const StreamConfig cfg, unsigned char *smem, Gate gate, Body body)
+						 const StreamConfig cfg, unsigned char *smem, Gate gate, Late late,
+						 Body body)
 {
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t total_warps = gridDim.x * kStreamWarps;
@@ -151,7 +159,10 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 	__syncwarp();
 
 	// producer (lane 0): fill stage `st` with slice `s`
-	auto issue = [&](uint32_t st, uint32_t s) {
+	auto issue = [&](uint32_t st, uint32_t v) {
+		uint32_t s = v + A.visit_shift;
+		if (s >= A.n_slices)
+			s -= A.n_slices;
 		const uint32_t off = __ldg(A.slice_off + s), width = __ldg(A.slice_off + s + 1) - off;
 		meta[st] = make_uint2(off, width);
 		unsigned char *dst = ring + (size_t)st * cfg.stage_bytes;
@@ -181,9 +192,22 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 	}
 
 	uint32_t n = 0;
+	bool late_done = false;
 	for (uint64_t s64 = first; s64 < A.n_slices; s64 += total_warps, n++) {
-		const uint32_t s = (uint32_t)s64;
+		uint32_t s = (uint32_t)s64 + A.visit_shift;
+		if (s >= A.n_slices)
+			s -= A.n_slices;
 		const uint32_t st = n % cfg.stages, parity = (n / cfg.stages) & 1u;
+		if (!late_done && s64 >= A.late_from) {
+			late_done = true;
+			if (!late()) {
+				// drain the stages that are in flight for visits n .. n + stages - 1
+				for (uint32_t a = 0; a < cfg.stages; a++)
+					if (s64 + (uint64_t)a * total_warps < A.n_slices)
+						mbar_wait(bars + (n + a) % cfg.stages, ((n + a) / cfg.stages) & 1u);
+				return;
+			}
+		}
 		mbar_wait(bars + st, parity);
 		const uint2 m = meta[st];
 		const uint32_t width = m.y;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kBlock, 2)
 spmv_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ x, double *__restrict__ y)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	sell_stream_rows<BLOCKED, false>(A, x, cfg, smem, [] { return true; }, [&](uint32_t row, double acc, double, double) {
+	sell_stream_rows<BLOCKED, false>(A, x, cfg, smem, [] { return true; }, [] { return true; }, [&](uint32_t row, double acc, double, double) {
 		if (row < A.N)
 			y[row] = acc;
 	});
@@ -118,7 +118,9 @@ int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out)
 	StreamConfig cfg;
 	const void *kernel = A->blocked ? (const void *)spmv_stream_kernel<true> : (const void *)spmv_stream_kernel<false>;
 	if (stream_config(A, kernel, &cfg)) {
-		const SellView V{A->N, A->n_slices, A->d_slice_off, A->d_val, A->blocked ? A->d_bcol : A->d_col};
+		SellView V;
+		V.N = A->N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
+		V.col = A->blocked ? A->d_bcol : A->d_col;
 		if (A->blocked)
 			spmv_stream_kernel<true><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
 		else
