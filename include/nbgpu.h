@@ -397,6 +397,10 @@ int nbgpu_dist_cg(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
 		  double *tolerance_reached);
 int nbgpu_dist_spmv(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
 		    const nbgpu_matrix_t *A_local, const double *d_in, double *d_out);
+/* device pointer to the window's input vector (N_loc owned entries, halo tail
+ * behind them): an SpMV caller that writes x there and passes it as d_in saves
+ * the copy into the window */
+double *nbgpu_dist_input_vector(nbgpu_dist_t *dist);
 
 #ifdef __cplusplus
 }

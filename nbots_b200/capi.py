@@ -111,6 +111,7 @@ SIGNATURES = {
                                         C.c_double, u32p, f64p]),
     "nbgpu_dist_cg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
                                 u32p, f64p]),
+    "nbgpu_dist_input_vector": (C.c_void_p, [C.c_void_p]),
     "nbgpu_dist_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

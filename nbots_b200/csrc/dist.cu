@@ -159,23 +159,18 @@ template <int NV, typename SlotOf>
 __device__ __forceinline__ bool cta_reduce_msgs(int world, SlotOf slot_of, unsigned long long seq, DistControl *mine,
 						unsigned long long timeout_ns, const int32_t *done, double (&tot)[NV])
 {
-	__shared__ int s_ok;
 	__shared__ double s_val[NV][kMaxRanks];
-	if (threadIdx.x == 0)
-		s_ok = !(done && *(volatile const int32_t *)done) && !*(volatile int *)&mine->error;
-	__syncthreads();
-	if (!s_ok)
-		return false;
-	__syncthreads();
+	int ok = 1;
 	if ((int)threadIdx.x < world * NV) {
+		// the pollers look at done / error themselves: one barrier for the whole step
+		ok = !(done && *(volatile const int32_t *)done) && !*(volatile int *)&mine->error;
 		const int r = threadIdx.x / NV, c = threadIdx.x % NV;
 		double v = 0.0;
-		if (!wait_msg(slot_of(r, c), seq, &v, mine, timeout_ns))
-			s_ok = 0;
+		if (ok)
+			ok = wait_msg(slot_of(r, c), seq, &v, mine, timeout_ns) ? 1 : 0;
 		s_val[c][r] = v;
 	}
-	__syncthreads();
-	if (!s_ok)
+	if (!__syncthreads_and(ok))
 		return false;
 #pragma unroll
 	for (int c = 0; c < NV; c++) {
@@ -901,6 +896,7 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 	SellView V;
 	V.N = N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
 	V.col = A->blocked ? A->d_bcol : A->d_col;
+	V.uniform_width = A->uniform_width;
 	V.visit_shift = P->visit_shift; V.late_from = P->late_from;
 	StreamConfig scfg, icfg;
 	const void *sk = A->blocked ? (const void *)dist_spmv_kernel<true> : (const void *)dist_spmv_kernel<false>;
@@ -1041,6 +1037,7 @@ int nbgpu_dist_spmv(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t 
 	SellView V;
 	V.N = A->N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
 	V.col = A->blocked ? A->d_bcol : A->d_col;
+	V.uniform_width = A->uniform_width;
 	V.visit_shift = P->visit_shift; V.late_from = P->late_from;
 	StreamConfig cfg;
 	const void *kern = A->blocked ? (const void *)dist_plain_spmv_kernel<true>
@@ -1051,7 +1048,8 @@ int nbgpu_dist_spmv(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t 
 	}
 	const unsigned long long seq = ++D->spmv_seq;
 	double *x_ext = D->x_ext();
-	NB_CUDA(cudaMemcpyAsync(x_ext, d_in, (size_t)A->N * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+	if (d_in != x_ext)   // callers that fill nbgpu_dist_input_vector() directly skip this copy
+		NB_CUDA(cudaMemcpyAsync(x_ext, d_in, (size_t)A->N * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 	const int n_dst = n_destinations(P);
 	if (n_dst)
 		NB_CUDA(launch(false, halo_push_kernel, n_dst, kBlock, 0, T, P->d_send_idx, (const double *)x_ext, 1, seq,
@@ -1065,6 +1063,12 @@ int nbgpu_dist_spmv(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t 
 			   (const double *)x_ext, d_out, D->d_ticket);
 	NB_CUDA(e);
 	return NBGPU_OK;
+}
+
+/* the window's input vector (owned part): SpMV callers may write x here and pass it as d_in */
+double *nbgpu_dist_input_vector(nbgpu_dist_t *D)
+{
+	return D ? D->x_ext() : nullptr;
 }
 
 /* communication error raised by a kernel wait (0 = none) */

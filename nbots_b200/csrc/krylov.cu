@@ -493,6 +493,7 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 	SellView V;
 	V.N = N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
 	V.col = A->blocked ? A->d_bcol : A->d_col;
+	V.uniform_width = A->uniform_width;
 	StreamConfig scfg, icfg;
 	const void *sk = A->blocked ? (const void *)krylov_spmv_stream_kernel<true>
 				    : (const void *)krylov_spmv_stream_kernel<false>;

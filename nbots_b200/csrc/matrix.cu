@@ -247,17 +247,29 @@ int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
 		A->h_row_ptr[i + 1] = A->h_row_ptr[i] + rows_size[i];
 	A->nnz = A->h_row_ptr[N];
 	A->n_slices = (N + kSliceRows - 1) / kSliceRows;
-	std::vector<uint32_t> off((size_t)A->n_slices + 1);
+	std::vector<uint32_t> off((size_t)A->n_slices + 1), width((size_t)A->n_slices);
 	uint64_t units = 0;
 	A->max_width = 0;
 	for (uint32_t s = 0; s < A->n_slices; s++) {
-		off[s] = (uint32_t)units;
 		uint32_t w = 0;
 		const uint32_t r1 = std::min<uint64_t>(N, (uint64_t)(s + 1) * kSliceRows);
 		for (uint32_t r = s * kSliceRows; r < r1; r++)
 			w = std::max(w, rows_size[r]);
+		width[s] = w;
 		A->max_width = std::max(A->max_width, w);
 		units += w;
+	}
+	// near-uniform rows (structured meshes): store every slice max_width wide
+	const uint64_t uniform_units = (uint64_t)A->n_slices * A->max_width;
+	A->uniform_width = 0;
+	if (!getenv("NBGPU_NO_UNIFORM") && A->n_slices > 0 && uniform_units <= units + units / 100) {
+		A->uniform_width = A->max_width;
+		std::fill(width.begin(), width.end(), A->max_width);
+	}
+	units = 0;
+	for (uint32_t s = 0; s < A->n_slices; s++) {
+		off[s] = (uint32_t)units;
+		units += width[s];
 		if (units > 0xFFFFFFFFull) {
 			set_error("matrix too large for 32-bit slice offsets");
 			return NBGPU_ERR_ARG;

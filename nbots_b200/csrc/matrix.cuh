@@ -23,6 +23,9 @@ struct nbgpu_matrix_s {
 	uint32_t n_slices = 0;
 	uint64_t stored = 0;                  // padded entry count = 32 * slice_off[n_slices]
 	uint32_t max_width = 0;
+	uint32_t uniform_width = 0;           // != 0: every slice is stored max_width wide (slice_off[s] = s * width);
+					      // chosen when that costs < 1 % extra entries, lets the kernels
+					      // compute slice offsets instead of loading them
 	uint32_t *d_slice_off = nullptr;      // [n_slices + 1]
 	double *d_val = nullptr;              // [stored]
 	uint32_t *d_col = nullptr;            // [stored]

@@ -114,6 +114,7 @@ struct SellView {
 	// and `late()` -- the wait for the halo -- is only called before visit index late_from.
 	uint32_t visit_shift = 0;
 	uint32_t late_from = 0xFFFFFFFFu;
+	uint32_t uniform_width = 0;   // != 0: slice s starts at s * uniform_width (no offset loads)
 };
 
 // Runs `body(row, acc, diag, x_row)` for every row of the slices this warp owns
@@ -163,7 +164,14 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		uint32_t s = v + A.visit_shift;
 		if (s >= A.n_slices)
 			s -= A.n_slices;
-		const uint32_t off = __ldg(A.slice_off + s), width = __ldg(A.slice_off + s + 1) - off;
+		uint32_t off, width;
+		if (A.uniform_width) {
+			off = s * A.uniform_width;
+			width = A.uniform_width;
+		} else {
+			off = __ldg(A.slice_off + s);
+			width = __ldg(A.slice_off + s + 1) - off;
+		}
 		meta[st] = make_uint2(off, width);
 		unsigned char *dst = ring + (size_t)st * cfg.stage_bytes;
 		const uint32_t vb = width * val_bytes_per_col, cb = width * col_bytes_per_col;

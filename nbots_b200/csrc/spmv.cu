@@ -121,6 +121,7 @@ int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out)
 		SellView V;
 		V.N = A->N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
 		V.col = A->blocked ? A->d_bcol : A->d_col;
+	V.uniform_width = A->uniform_width;
 		if (A->blocked)
 			spmv_stream_kernel<true><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
 		else
