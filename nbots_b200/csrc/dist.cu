@@ -66,6 +66,7 @@ struct DistState {
 	uint32_t k_final;
 	int32_t done;
 	unsigned int ticket;
+	unsigned int push_ticket;   // halo pushes (separate from the reductions' ticket: both live in K1)
 };
 
 struct PeerTable {
@@ -182,50 +183,67 @@ __device__ __forceinline__ bool cta_reduce_msgs(int world, SlotOf slot_of, unsig
 	return true;
 }
 
-// ---- halo push: one CTA per destination ----------------------------------------
-// which: 0 -> p (halo_seq), 1 -> x/input vector (xh_seq, waits for the consumer's ack first)
-__global__ void __launch_bounds__(kBlock)
+// ---- halo push ---------------------------------------------------------------------
+// The send list (boundary entries of v, grouped by destination) is split evenly over
+// the CTAs of the calling kernel; in each CTA ONE warp copies its piece into the
+// neighbours' halo tails with plain NVLink stores, fences at system scope and takes a
+// ticket; the last arriver raises the destinations' flags.  Other warps of the CTA
+// are not held up.  Cost is independent of the halo size up to ~grid x 32 entries
+// per trip (the round-1 first version pushed from a single CTA: 60 us for a 64 KB
+// halo).  which: 0 -> p (halo_seq), 1 -> input vector (xh_seq; waits for the
+// destination's ack of the previous push first, the input halo is single-buffered).
+__device__ __forceinline__ void push_halo_piece(const PeerTable &T, const uint32_t *__restrict__ send_idx,
+						const double *v, int which, unsigned long long seq,
+						unsigned int *ticket)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t total = T.send_ptr[T.world];
+	DistControl *mine = T.ctrl[T.rank];
+	const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+	const uint32_t b = min(total, blockIdx.x * per), e = min(total, b + per);
+	bool ok = true;
+	if (which == 1 && e > b) {
+		// destinations touched by [b, e)
+		for (int d = 0; d < T.world && ok; d++)
+			if (T.send_ptr[d] < e && T.send_ptr[d + 1] > b) {
+				int w = 1;
+				if (lane == 0)
+					w = wait_seq(&mine->xh_ack[d], seq - 1, mine, T.timeout_ns) ? 1 : 0;
+				ok = __shfl_sync(0xffffffffu, w, 0) != 0;
+			}
+	}
+	if (ok) {
+		for (uint32_t j = b + lane; j < e; j += 32) {
+			int d = 0;
+			while (j >= T.send_ptr[d + 1])
+				d++;
+			double *dst = which ? T.x_halo_dst[d] : T.p_halo_dst[d];
+			dst[j - T.send_ptr[d]] = v[send_idx[j]];
+		}
+		if (e > b)
+			__threadfence_system();
+	}
+	__syncwarp();
+	if (lane == 0) {
+		const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+		if (t == gridDim.x - 1) {
+			__threadfence_system();
+			for (int d = 0; d < T.world; d++)
+				if (T.send_ptr[d + 1] > T.send_ptr[d])
+					st_release_sys(which ? &T.ctrl[d]->xh_seq[T.rank] : &T.ctrl[d]->halo_seq[T.rank], seq);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(32)
 halo_push_kernel(PeerTable T, const uint32_t *__restrict__ send_idx, const double *__restrict__ v, int which,
-		 unsigned long long seq, const DistState *st)
+		 unsigned long long seq, unsigned int *ticket)
 {
 	pdl_wait();
 	pdl_launch_dependents();
-	DistControl *mine = T.ctrl[T.rank];
-	__shared__ int go;
-	if (threadIdx.x == 0)
-		go = !(st && *(volatile const int32_t *)&st->done) && !*(volatile int *)&mine->error;
-	__syncthreads();
-	if (!go)
+	if (*(volatile int *)&T.ctrl[T.rank]->error)
 		return;
-	// destinations are enumerated by blockIdx among the ranks with a non-empty send list
-	int d = -1, seen = 0;
-	for (int r = 0; r < T.world; r++)
-		if (T.send_ptr[r + 1] > T.send_ptr[r]) {
-			if (seen == (int)blockIdx.x)
-				d = r;
-			seen++;
-		}
-	if (d < 0)
-		return;
-	if (which == 1) {
-		// single-buffered input halo: the destination must have consumed my previous push
-		__shared__ int ok;
-		if (threadIdx.x == 0)
-			ok = wait_seq(&mine->xh_ack[d], seq - 1, mine, T.timeout_ns) ? 1 : 0;
-		__syncthreads();
-		if (!ok)
-			return;
-	}
-	double *dst = which ? T.x_halo_dst[d] : T.p_halo_dst[d];
-	const uint32_t b = T.send_ptr[d], e = T.send_ptr[d + 1];
-	for (uint32_t j = b + threadIdx.x; j < e; j += blockDim.x)
-		dst[j - b] = v[send_idx[j]];
-	__threadfence_system();
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		DistControl *peer = T.ctrl[d];
-		st_release_sys(which ? &peer->xh_seq[T.rank] : &peer->halo_seq[T.rank], seq);
-	}
+	push_halo_piece(T, send_idx, v, which, seq, ticket);
 }
 
 // post NV partial values into slot `rank` of every peer (called by one CTA, after its reduction)
@@ -339,7 +357,8 @@ __global__ void dist_init_reduce_kernel(PeerTable T, unsigned long long seq, Dis
 template <bool BLOCKED>
 __global__ void __launch_bounds__(kBlock, 2)
 dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned long long base,
-		 const double *__restrict__ p_ext, double *__restrict__ w, double *partials, DistState *st)
+		 const uint32_t *__restrict__ send_idx, const double *__restrict__ p_ext, double *__restrict__ w,
+		 double *partials, DistState *st)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[1] = {0.0};
@@ -348,6 +367,11 @@ dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned
 		A, p_ext, cfg, smem,
 		[&] {
 			active = iteration_gate(k, st) && !*(volatile int *)&T.ctrl[T.rank]->error;
+			// the boundary entries of p_k leave at the START of the kernel that consumes p_k
+			// (warp 0 of every CTA sends a piece while the other warps already stream the matrix);
+			// the neighbours only need them for their last slices (late wait below)
+			if (active && (threadIdx.x >> 5) == 0 && T.send_ptr[T.world] > 0)
+				push_halo_piece(T, send_idx, p_ext, 0, base + k + 1, &st->push_ticket);
 			return active;
 		},
 		[&] { return warp_wait_halo(T, 0, base + k + 1); },   // only the slices that read halo columns wait
@@ -440,14 +464,18 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		post_gq(T, tot[0], JACOBI ? tot[1] : tot[0], base + k + 2);
 }
 
-// ---- K3: waits for all (g.g, g.q), p = -q + beta p, pushes the boundary of p --------
-// The CTA that finishes last (ticket) sends this rank's boundary entries of the new p
-// into the neighbours' halo tails and raises their flags: the exchange is part of the
-// kernel that produces the data, no separate launch.
+// ---- K3: waits for all (g.g, g.q), p = -q + beta p ---------------------------------
 __global__ void __launch_bounds__(kBlock)
 dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, const double *__restrict__ q,
-		double *__restrict__ p, const uint32_t *__restrict__ send_idx, DistState *st)
+		double *__restrict__ p, DistState *st)
 {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t base_i = blockIdx.x * blockDim.x + threadIdx.x;
+	double p0 = 0, p1 = 0;
+	if (base_i < N) {
+		p0 = p[base_i];
+		p1 = p[base_i + stride < N ? base_i + stride : base_i];
+	}
 	pdl_wait();
 	pdl_launch_dependents();
 	DistControl *mine = T.ctrl[T.rank];
@@ -461,38 +489,19 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 		st->gg[(k + 1) % 3u] = gg;
 		st->gq[(k + 1) & 1] = gq;
 	}
-	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < N; i0 += 2 * stride) {
+	for (uint32_t i0 = base_i; i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
-		const double q0 = q[i0], p0 = p[i0], q1 = q[j1], p1 = p[j1];
+		if (i0 != base_i) {
+			p0 = p[i0];
+			p1 = p[j1];
+		}
+		const double q0 = q[i0], q1 = q[j1];
 		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, p0));
 		if (has1)
 			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
 	}
-	if (T.send_ptr[T.world] == 0)
-		return;
-	__shared__ bool last;
-	__threadfence();
-	__syncthreads();
-	if (threadIdx.x == 0)
-		last = atomicInc(&st->ticket, gridDim.x - 1) == gridDim.x - 1;
-	__syncthreads();
-	if (!last)
-		return;
-	__threadfence();
-	const uint32_t total = T.send_ptr[T.world];
-	for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
-		int d = 0;
-		while (j >= T.send_ptr[d + 1])
-			d++;
-		T.p_halo_dst[d][j - T.send_ptr[d]] = __ldcg(p + send_idx[j]);
-	}
-	__threadfence_system();
-	__syncthreads();
-	if ((int)threadIdx.x < T.world && T.send_ptr[threadIdx.x + 1] > T.send_ptr[threadIdx.x])
-		st_release_sys(&T.ctrl[threadIdx.x]->halo_seq[T.rank], base + k + 2);
 }
 
 // ---- distributed SpMV (config 3): y = A x with the halo of x exchanged first --------
@@ -760,9 +769,9 @@ int nbgpu_dist_create(int rank, int world, size_t ext_len, void *ipc_handle_out,
 	if (e == cudaSuccess)
 		e = cudaMalloc(&D->d_state, sizeof(DistState));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&D->d_ticket, sizeof(unsigned int));
+		e = cudaMalloc(&D->d_ticket, 4 * sizeof(unsigned int));
 	if (e == cudaSuccess)
-		e = cudaMemset(D->d_ticket, 0, sizeof(unsigned int));
+		e = cudaMemset(D->d_ticket, 0, 4 * sizeof(unsigned int));
 	if (e == cudaSuccess)
 		e = cudaMallocHost(&D->h_state, 4 * sizeof(DistState) + 64);
 	if (e == cudaSuccess)
@@ -919,9 +928,10 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 	const unsigned long long base = D->seq_base;
 
 	// x halo -> init
+	const int push_grid = std::max(1, (int)std::min<uint32_t>((P->send_ptr[P->world] + 31) / 32, 1024));
 	if (n_dst)
-		NB_CUDA(launch(false, halo_push_kernel, n_dst, kBlock, 0, T, P->d_send_idx, x_ext, 1, xseq,
-			       (const DistState *)nullptr));
+		NB_CUDA(launch(false, halo_push_kernel, push_grid, 32, 0, T, (const uint32_t *)P->d_send_idx,
+			       (const double *)x_ext, 1, xseq, D->d_ticket + 1));
 	cudaError_t e;
 	// the init kernel waits for the x halo (xseq) and posts its dots as sequence base + 1
 	if (jacobi && A->blocked)
@@ -938,10 +948,6 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 			   x_ext, g, p, q, diag, c.partials, st);
 	NB_CUDA(e);
 	NB_CUDA(launch(false, dist_init_reduce_kernel, 1, 32, 0, T, base + 1, st));
-	if (n_dst)
-		NB_CUDA(launch(false, halo_push_kernel, n_dst, kBlock, 0, T, P->d_send_idx, (const double *)p, 0, base + 1,
-			       (const DistState *)st));
-
 	uint32_t k = 0;
 	int slot = 0;
 	bool pending[2] = {false, false};
@@ -951,10 +957,10 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 		for (; k < k_end; k++) {
 			if (A->blocked)
 				e = launch(pdl, dist_spmv_kernel<true>, scfg.grid, kBlock, scfg.smem_bytes, k, V, scfg, T, base,
-					   (const double *)p, w, c.partials, st);
+					   (const uint32_t *)P->d_send_idx, (const double *)p, w, c.partials, st);
 			else
 				e = launch(pdl, dist_spmv_kernel<false>, scfg.grid, kBlock, scfg.smem_bytes, k, V, scfg, T, base,
-					   (const double *)p, w, c.partials, st);
+					   (const uint32_t *)P->d_send_idx, (const double *)p, w, c.partials, st);
 			NB_CUDA(e);
 			if (jacobi)
 				e = launch(pdl, dist_update_kernel<true>, ugrid, kBlock, 0, k, N, T, base, (const double *)p, w,
@@ -963,16 +969,15 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 				e = launch(pdl, dist_update_kernel<false>, ugrid, kBlock, 0, k, N, T, base, (const double *)p, w,
 					   diag, xw, g, q, c.partials, st);
 			NB_CUDA(e);
-			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p,
-				       (const uint32_t *)P->d_send_idx, st));
+			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p, st));
 		}
 		if (k == max_iter) {
 			if (A->blocked)
 				e = launch(false, dist_spmv_kernel<true>, scfg.grid, kBlock, scfg.smem_bytes, k, V, scfg, T, base,
-					   (const double *)p, w, c.partials, st);
+					   (const uint32_t *)P->d_send_idx, (const double *)p, w, c.partials, st);
 			else
 				e = launch(false, dist_spmv_kernel<false>, scfg.grid, kBlock, scfg.smem_bytes, k, V, scfg, T, base,
-					   (const double *)p, w, c.partials, st);
+					   (const uint32_t *)P->d_send_idx, (const double *)p, w, c.partials, st);
 			NB_CUDA(e);
 		}
 		NB_CUDA(cudaMemcpyAsync(&hst[slot], st, sizeof(DistState), cudaMemcpyDeviceToHost, c.stream));
@@ -1051,9 +1056,10 @@ int nbgpu_dist_spmv(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t 
 	if (d_in != x_ext)   // callers that fill nbgpu_dist_input_vector() directly skip this copy
 		NB_CUDA(cudaMemcpyAsync(x_ext, d_in, (size_t)A->N * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 	const int n_dst = n_destinations(P);
+	const int push_grid = std::max(1, (int)std::min<uint32_t>((P->send_ptr[P->world] + 31) / 32, 1024));
 	if (n_dst)
-		NB_CUDA(launch(false, halo_push_kernel, n_dst, kBlock, 0, T, P->d_send_idx, (const double *)x_ext, 1, seq,
-			       (const DistState *)nullptr));
+		NB_CUDA(launch(false, halo_push_kernel, push_grid, 32, 0, T, (const uint32_t *)P->d_send_idx,
+			       (const double *)x_ext, 1, seq, D->d_ticket + 1));
 	cudaError_t e;
 	if (A->blocked)
 		e = launch(false, dist_plain_spmv_kernel<true>, cfg.grid, kBlock, cfg.smem_bytes, V, cfg, T, seq,
