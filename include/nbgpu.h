@@ -325,6 +325,30 @@ int nbgpu_fem_static_elasticity2d_lists(const nbgpu_mesh_desc_t *mesh,
 					double solver_tol, double *displacement,
 					double *strain, nbgpu_fem_report_t *report);
 
+/* Device-resident session for repeated assembly + solve on one mesh (the call
+ * pattern of the reference's damage loop, static_damage2D.c:300-460, and of a
+ * SIMP topology-optimisation loop): pattern, matrix and mesh are built once;
+ * each step re-assembles with an optional enabled mask (pipeline.c:93-98) and
+ * optional per-element stiffness factors, re-applies the boundary conditions
+ * and runs Jacobi-PCG, warm-started from the previous displacement if asked.
+ * max_iter 0 = N, solver_tol <= 0 = 1e-8 (static_elasticity2D.c:88-90). */
+typedef struct nbgpu_fem_session_s nbgpu_fem_session_t;
+int nbgpu_fem_session_create(const nbgpu_mesh_desc_t *mesh,
+			     const nbgpu_elem_tables_t *tables, const double D[4],
+			     double density, uint32_t n_neumann,
+			     const uint32_t *neumann_dof, const double *neumann_add,
+			     uint32_t n_dirichlet, const uint32_t *dirichlet_dof,
+			     const double *dirichlet_val, int self_weight,
+			     const double gravity[2], double thickness,
+			     int assembly_mode, nbgpu_fem_session_t **out);
+int nbgpu_fem_session_step(nbgpu_fem_session_t *session, const uint8_t *enabled,
+			   const double *elem_scale, int warm_start,
+			   uint32_t max_iter, double solver_tol,
+			   nbgpu_fem_report_t *report);
+int nbgpu_fem_session_results(nbgpu_fem_session_t *session, double *displacement,
+			      double *strain);
+int nbgpu_fem_session_destroy(nbgpu_fem_session_t *session);
+
 int nbgpu_fem_static_elasticity2d(const nbgpu_mesh_desc_t *mesh,
 				  const nbgpu_elem_tables_t *tables,
 				  double E, double poisson, double density,

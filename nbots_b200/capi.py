@@ -96,6 +96,11 @@ SIGNATURES = {
     "nbgpu_apply_dirichlet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p, f64p]),
     "nbgpu_compute_strain": (C.c_int, [C.c_void_p, C.POINTER(ElemTables), C.c_void_p, C.c_void_p]),
     "nbgpu_stress_from_strain": (C.c_int, [C.c_uint32, C.c_uint32, f64p, f64p, u8p, C.c_void_p, C.c_void_p]),
+    "nbgpu_fem_session_create": (C.c_int, [C.c_void_p, C.c_void_p, f64p, C.c_double, C.c_uint32, u32p, f64p, C.c_uint32,
+                                           u32p, f64p, C.c_int, f64p, C.c_double, C.c_int, vpp]),
+    "nbgpu_fem_session_step": (C.c_int, [C.c_void_p, u8p, f64p, C.c_int, C.c_uint32, C.c_double, C.c_void_p]),
+    "nbgpu_fem_session_results": (C.c_int, [C.c_void_p, f64p, f64p]),
+    "nbgpu_fem_session_destroy": (C.c_int, [C.c_void_p]),
     "nbgpu_matrix_create_local": (C.c_int, [C.c_uint32, C.c_uint32, u32p, u32p, f64p, vpp]),
     "nbgpu_dist_plan_create": (C.c_int, [C.c_int, C.c_int, u32p, u32p, u32p, vpp]),
     "nbgpu_dist_plan_destroy": (C.c_int, [C.c_void_p]),

@@ -171,6 +171,179 @@ int nbgpu_fem_static_elasticity2d(const nbgpu_mesh_desc_t *md, const nbgpu_elem_
 						   assembly_mode, solver_tol, displacement, strain, report);
 }
 
+/* ---- device-resident session: pattern, matrix and mesh are built once; every step
+ * re-assembles (optionally with an enabled mask / per-element stiffness factors),
+ * re-applies the boundary conditions and solves, warm-started from the previous
+ * displacement if asked.  This is the call pattern of the reference's repeated
+ * assembly + PCG loop (static_damage2D.c:300-460, void-material hook
+ * pipeline.c:93-98) and of a SIMP topology-optimisation loop (BASELINE.json
+ * configs[4]); the one-shot driver below is a session with a single step. */
+struct nbgpu_fem_session_s {
+	uint32_t N = 0, n_gp = 0, N_elems = 0;
+	uint64_t nnz = 0;
+	nbgpu_matrix_t *K = nullptr;
+	nbgpu_mesh_t *mesh = nullptr;
+	double *d_vec = nullptr, *d_F = nullptr, *d_x = nullptr, *d_strain = nullptr;
+	nbgpu_elem_tables_t tables;
+	nbgpu_assembly_params_t ap;
+	std::vector<uint32_t> neu_dof, dir_dof;
+	std::vector<double> neu_add, dir_val;
+	double ms_pattern = 0, ms_upload = 0;
+	bool have_x = false;
+};
+
+int nbgpu_fem_session_destroy(nbgpu_fem_session_t *S)
+{
+	if (!S)
+		return NBGPU_OK;
+	nbgpu_free(S->d_vec);
+	nbgpu_mesh_destroy(S->mesh);
+	nbgpu_matrix_destroy(S->K);
+	delete S;
+	return NBGPU_OK;
+}
+
+int nbgpu_fem_session_create(const nbgpu_mesh_desc_t *md, const nbgpu_elem_tables_t *tables, const double D[4],
+			     double density, uint32_t n_neu, const uint32_t *neu_dof, const double *neu_add,
+			     uint32_t n_dir, const uint32_t *dir_dof, const double *dir_val, int self_weight,
+			     const double gravity[2], double thickness, int assembly_mode, nbgpu_fem_session_t **out)
+{
+	NB_INIT();
+	NB_ARG(md != nullptr && out != nullptr && D != nullptr);
+	NB_ARG(md->nodes_per_elem == 3 || md->nodes_per_elem == 4);
+	NB_ARG(!self_weight || gravity != nullptr);
+	nbgpu_fem_session_t *S = new nbgpu_fem_session_t();
+	S->N = 2 * md->N_nod;
+	S->n_gp = md->nodes_per_elem == 4 ? 4 : 1;
+	S->N_elems = md->N_elems;
+	int st = NBGPU_OK;
+	if (tables)
+		S->tables = *tables;
+	else
+		st = nbgpu_elem_tables_default(md->nodes_per_elem, &S->tables);
+	memset(&S->ap, 0, sizeof(S->ap));
+	memcpy(S->ap.D, D, sizeof(S->ap.D));
+	for (int k = 0; k < 4; k++)
+		S->ap.D_void[k] = 1e-6;          // pipeline.c:93
+	S->ap.density = density;
+	S->ap.density_void = 1e-6;               // pipeline.c:94
+	S->ap.thickness = thickness;
+	S->ap.self_weight = self_weight != 0;
+	if (self_weight) {
+		S->ap.gravity[0] = gravity[0];
+		S->ap.gravity[1] = gravity[1];
+	}
+	S->ap.mode = assembly_mode;
+	S->neu_dof.assign(neu_dof, neu_dof + n_neu);
+	S->neu_add.assign(neu_add, neu_add + n_neu);
+	S->dir_dof.assign(dir_dof, dir_dof + n_dir);
+	S->dir_val.assign(dir_val, dir_val + n_dir);
+
+	// (1) graph + sparsity pattern (static_elasticity2D.c:45-50)
+	double t0 = now_ms();
+	std::vector<uint32_t> rows_size(S->N), cols;
+	if (st == NBGPU_OK)
+		st = nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
+					     rows_size.data(), nullptr, &S->nnz);
+	if (st == NBGPU_OK) {
+		cols.resize(S->nnz);
+		st = nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
+					     rows_size.data(), cols.data(), &S->nnz);
+	}
+	S->ms_pattern = now_ms() - t0;
+
+	// (2) device objects
+	t0 = now_ms();
+	const size_t n_strain = (size_t)3 * S->n_gp * md->N_elems;
+	if (st == NBGPU_OK)
+		st = nbgpu_matrix_create_from_csr(S->N, rows_size.data(), cols.data(), nullptr, &S->K);
+	if (st == NBGPU_OK)
+		st = nbgpu_mesh_create(md->N_nod, md->nod, md->N_elems, md->nodes_per_elem, md->adj, &S->mesh);
+	if (st == NBGPU_OK)
+		st = nbgpu_malloc((void **)&S->d_vec, (2 * (size_t)S->N + n_strain) * sizeof(double));
+	if (st == NBGPU_OK) {
+		S->d_F = S->d_vec;
+		S->d_x = S->d_vec + S->N;
+		S->d_strain = S->d_vec + 2 * (size_t)S->N;
+		st = nbgpu_sync();
+	}
+	S->ms_upload = now_ms() - t0;
+	if (st != NBGPU_OK) {
+		nbgpu_fem_session_destroy(S);
+		return st;
+	}
+	*out = S;
+	return NBGPU_OK;
+}
+
+int nbgpu_fem_session_step(nbgpu_fem_session_t *S, const uint8_t *enabled, const double *elem_scale, int warm_start,
+			   uint32_t max_iter, double solver_tol, nbgpu_fem_report_t *report)
+{
+	NB_INIT();
+	NB_ARG(S != nullptr);
+	nbgpu_fem_report_t rep;
+	memset(&rep, 0, sizeof(rep));
+	rep.N = S->N;
+	rep.nnz = S->nnz;
+	rep.ms_pattern = S->ms_pattern;
+	rep.ms_upload = S->ms_upload;
+	// (3) assembly (static_elasticity2D.c:58-65)
+	double t0 = now_ms();
+	int status = 0;
+	int st = nbgpu_assemble_elasticity2d(S->K, S->mesh, &S->tables, &S->ap, enabled, elem_scale, S->d_F, nullptr);
+	if (st == NBGPU_DISTORTED_ELEMENT) {
+		status = 1;                   // static_elasticity2D.c:62-65
+		st = NBGPU_OK;
+	}
+	if (st == NBGPU_OK)
+		st = nbgpu_sync();
+	rep.ms_assembly = now_ms() - t0;
+	// (4) boundary conditions (static_elasticity2D.c:67)
+	if (st == NBGPU_OK && status == 0) {
+		t0 = now_ms();
+		st = nbgpu_vector_add_entries(S->d_F, (uint32_t)S->neu_dof.size(), S->neu_dof.data(), S->neu_add.data());
+		if (st == NBGPU_OK)
+			st = nbgpu_apply_dirichlet(S->K, S->d_F, (uint32_t)S->dir_dof.size(), S->dir_dof.data(),
+						   S->dir_val.data());
+		rep.ms_bcond = now_ms() - t0;
+	}
+	// (5) solver(): x0 = 0 (or the previous displacement), abs tol; 0 and 1 both accepted (:83-97)
+	if (st == NBGPU_OK && status == 0) {
+		t0 = now_ms();
+		if (!warm_start || !S->have_x)
+			st = nbgpu_memset(S->d_x, 0, (size_t)S->N * sizeof(double));
+		if (st == NBGPU_OK) {
+			int sst = nbgpu_pcg_jacobi(S->K, S->d_F, S->d_x, max_iter ? max_iter : S->N,
+						   solver_tol > 0 ? solver_tol : 1e-8, &rep.solver_iters, &rep.solver_residual);
+			if (sst == NBGPU_OK || sst == NBGPU_NOT_CONVERGED) {
+				rep.solver_status = sst;
+				S->have_x = true;
+			} else {
+				st = sst;
+			}
+		}
+		rep.ms_solve = now_ms() - t0;
+	}
+	if (report)
+		*report = rep;
+	return st != NBGPU_OK ? st : status;
+}
+
+/* displacement[N] and, if not NULL, strain[3 N_gp N_elems] of the last step (pipeline.c:266-319) */
+int nbgpu_fem_session_results(nbgpu_fem_session_t *S, double *displacement, double *strain)
+{
+	NB_INIT();
+	NB_ARG(S != nullptr && S->have_x);
+	int st = NBGPU_OK;
+	if (strain)
+		st = nbgpu_compute_strain(S->mesh, &S->tables, S->d_x, S->d_strain);
+	if (st == NBGPU_OK && displacement)
+		st = nbgpu_copy_d2h(displacement, S->d_x, (size_t)S->N * sizeof(double));
+	if (st == NBGPU_OK && strain)
+		st = nbgpu_copy_d2h(strain, S->d_strain, (size_t)3 * S->n_gp * S->N_elems * sizeof(double));
+	return st;
+}
+
 int nbgpu_fem_static_elasticity2d_lists(const nbgpu_mesh_desc_t *md, const nbgpu_elem_tables_t *tables,
 					const double D[4], double density, uint32_t n_neu, const uint32_t *neu_dof,
 					const double *neu_add, uint32_t n_dir, const uint32_t *dir_dof,
@@ -179,119 +352,24 @@ int nbgpu_fem_static_elasticity2d_lists(const nbgpu_mesh_desc_t *md, const nbgpu
 					int assembly_mode, double solver_tol, double *displacement,
 					double *strain, nbgpu_fem_report_t *report)
 {
-	NB_INIT();
-	NB_ARG(md != nullptr && displacement != nullptr && D != nullptr);
-	NB_ARG(md->nodes_per_elem == 3 || md->nodes_per_elem == 4);
-	NB_ARG(!self_weight || gravity != nullptr);
+	NB_ARG(displacement != nullptr);
+	(void)analysis2D;   // D already carries the (always plane-stress, formulas.c:38-45) material law
+	nbgpu_fem_session_t *S = nullptr;
+	NB_TRY(nbgpu_fem_session_create(md, tables, D, density, n_neu, neu_dof, neu_add, n_dir, dir_dof, dir_val,
+					self_weight, gravity, thickness, assembly_mode, &S));
 	nbgpu_fem_report_t rep;
 	memset(&rep, 0, sizeof(rep));
-	const uint32_t N = 2 * md->N_nod;
-	const uint32_t n_gp = md->nodes_per_elem == 4 ? 4 : 1;
-	nbgpu_elem_tables_t default_tables;
-	if (!tables) {
-		NB_TRY(nbgpu_elem_tables_default(md->nodes_per_elem, &default_tables));
-		tables = &default_tables;
-	}
-
-	// (1) graph + sparsity pattern (static_elasticity2D.c:45-50)
-	double t0 = now_ms();
-	std::vector<uint32_t> rows_size(N), cols;
-	uint64_t nnz = 0;
-	NB_TRY(nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
-				       rows_size.data(), nullptr, &nnz));
-	cols.resize(nnz);
-	NB_TRY(nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
-				       rows_size.data(), cols.data(), &nnz));
-	rep.N = N;
-	rep.nnz = nnz;
-	rep.ms_pattern = now_ms() - t0;
-
-	// (2) device objects
-	t0 = now_ms();
-	nbgpu_matrix_t *K = nullptr;
-	nbgpu_mesh_t *mesh = nullptr;
-	double *d_vec = nullptr;   // F | x | strain
-	const size_t n_strain = (size_t)3 * n_gp * md->N_elems;
-	int st = nbgpu_matrix_create_from_csr(N, rows_size.data(), cols.data(), nullptr, &K);
-	std::vector<uint32_t>().swap(cols);
-	if (st == NBGPU_OK)
-		st = nbgpu_mesh_create(md->N_nod, md->nod, md->N_elems, md->nodes_per_elem, md->adj, &mesh);
-	if (st == NBGPU_OK)
-		st = nbgpu_malloc((void **)&d_vec, (2 * (size_t)N + n_strain) * sizeof(double));
-	double *d_F = d_vec, *d_x = d_vec + N, *d_strain = d_vec + 2 * (size_t)N;
-	if (st == NBGPU_OK)
-		st = nbgpu_sync();
-	rep.ms_upload = now_ms() - t0;
-
-	// (3) assembly (static_elasticity2D.c:58-65)
-	int status = 0;
+	int st = nbgpu_fem_session_step(S, enabled, nullptr, 0, 0, solver_tol, &rep);
 	if (st == NBGPU_OK) {
-		t0 = now_ms();
-		nbgpu_assembly_params_t ap;
-		memset(&ap, 0, sizeof(ap));
-		memcpy(ap.D, D, sizeof(ap.D));
-		(void)analysis2D;
-		for (int k = 0; k < 4; k++)
-			ap.D_void[k] = 1e-6;          // pipeline.c:93
-		ap.density = density;
-		ap.density_void = 1e-6;               // pipeline.c:94
-		ap.thickness = thickness;
-		ap.self_weight = self_weight != 0;
-		if (self_weight) {
-			ap.gravity[0] = gravity[0];
-			ap.gravity[1] = gravity[1];
-		}
-		ap.mode = assembly_mode;
-		st = nbgpu_assemble_elasticity2d(K, mesh, tables, &ap, enabled, nullptr, d_F, nullptr);
-		if (st == NBGPU_DISTORTED_ELEMENT) {
-			status = 1;                   // static_elasticity2D.c:62-65
-			st = NBGPU_OK;
-		}
-		rep.ms_assembly = now_ms() - t0;
-	}
-
-	// (4) boundary conditions (static_elasticity2D.c:67)
-	if (st == NBGPU_OK && status == 0) {
-		t0 = now_ms();
-		if (st == NBGPU_OK)
-			st = nbgpu_vector_add_entries(d_F, n_neu, neu_dof, neu_add);
-		if (st == NBGPU_OK)
-			st = nbgpu_apply_dirichlet(K, d_F, n_dir, dir_dof, dir_val);
-		rep.ms_bcond = now_ms() - t0;
-	}
-
-	// (5) solver(): x0 = 0, max_iter = N, abs tol 1e-8; 0 and 1 both accepted (:83-97)
-	if (st == NBGPU_OK && status == 0) {
-		t0 = now_ms();
-		st = nbgpu_memset(d_x, 0, (size_t)N * sizeof(double));
-		if (st == NBGPU_OK) {
-			int sst = nbgpu_pcg_jacobi(K, d_F, d_x, N, solver_tol > 0 ? solver_tol : 1e-8,
-						   &rep.solver_iters, &rep.solver_residual);
-			if (sst == NBGPU_OK || sst == NBGPU_NOT_CONVERGED)
-				rep.solver_status = sst;
-			else
-				st = sst;
-		}
-		rep.ms_solve = now_ms() - t0;
-	}
-
-	// (6) strain at the Gauss points (:75) and results back to the caller
-	if (st == NBGPU_OK && status == 0) {
-		t0 = now_ms();
-		if (strain)
-			st = nbgpu_compute_strain(mesh, tables, d_x, d_strain);
-		if (st == NBGPU_OK)
-			st = nbgpu_copy_d2h(displacement, d_x, (size_t)N * sizeof(double));
-		if (st == NBGPU_OK && strain)
-			st = nbgpu_copy_d2h(strain, d_strain, n_strain * sizeof(double));
+		// (6) strain at the Gauss points (:75) and results back to the caller
+		const double t0 = now_ms();
+		st = nbgpu_fem_session_results(S, displacement, strain);
 		rep.ms_post = now_ms() - t0;
 	}
-	nbgpu_free(d_vec);
-	nbgpu_mesh_destroy(mesh);
-	nbgpu_matrix_destroy(K);
+	nbgpu_fem_session_destroy(S);
 	if (report)
 		*report = rep;
-	return st != NBGPU_OK ? st : status;
+	return st;
 }
 
 }  // extern "C"

@@ -81,6 +81,16 @@ int nbo_assemble(uint32_t N_nod, const double *nod, uint32_t N_elems,
 		 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
 		 double *F);
 
+/* nbo_assemble with the product's per-element stiffness factor (not a reference
+ * feature; checker for the SIMP-style hook only) */
+int nbo_assemble_scaled(uint32_t N_nod, const double *nod, uint32_t N_elems,
+			int elem_type, const uint32_t *adj, double E, double nu,
+			double density, int self_weight, double gx, double gy,
+			int analysis, double thickness, const uint8_t *enabled,
+			const double *elem_scale,
+			const uint64_t *row_ptr, const uint32_t *cols, double *vals,
+			double *F);
+
 /* Boundary-condition record, one per nb_bcond_push (bcond.c:153-165) */
 typedef struct {
 	int32_t kind;      /* 0 Dirichlet, 1 Neumann                         */

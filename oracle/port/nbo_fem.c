@@ -107,12 +107,49 @@ static double jacobian_and_gradients(const elem_t *el, const double *nod,
  * (material choice: disabled elements get D = {1e-6 x4}, density 1e-6),
  * :124-172 (Gauss loop, stop at detJ < 0), :174-230 (B'DB accumulation,
  * expression order kept), :232-264 (scatter by node pairs). */
+static int assemble_impl(uint32_t N_nod, const double *nod, uint32_t N_elems,
+			 int elem_type, const uint32_t *adj, double E, double nu,
+			 double density, int self_weight, double gx, double gy,
+			 int analysis, double thickness, const uint8_t *enabled,
+			 const double *elem_scale,
+			 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
+			 double *F);
+
 int nbo_assemble(uint32_t N_nod, const double *nod, uint32_t N_elems,
 		 int elem_type, const uint32_t *adj, double E, double nu,
 		 double density, int self_weight, double gx, double gy,
 		 int analysis, double thickness, const uint8_t *enabled,
 		 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
 		 double *F)
+{
+	return assemble_impl(N_nod, nod, N_elems, elem_type, adj, E, nu, density,
+			     self_weight, gx, gy, analysis, thickness, enabled,
+			     NULL, row_ptr, cols, vals, F);
+}
+
+/* Extension used only to check the product's SIMP-style hook (the reference has
+ * no such parameter): the constitutive matrix of every ENABLED element is
+ * multiplied by elem_scale[e] before integration; everything else as above. */
+int nbo_assemble_scaled(uint32_t N_nod, const double *nod, uint32_t N_elems,
+			int elem_type, const uint32_t *adj, double E, double nu,
+			double density, int self_weight, double gx, double gy,
+			int analysis, double thickness, const uint8_t *enabled,
+			const double *elem_scale,
+			const uint64_t *row_ptr, const uint32_t *cols, double *vals,
+			double *F)
+{
+	return assemble_impl(N_nod, nod, N_elems, elem_type, adj, E, nu, density,
+			     self_weight, gx, gy, analysis, thickness, enabled,
+			     elem_scale, row_ptr, cols, vals, F);
+}
+
+static int assemble_impl(uint32_t N_nod, const double *nod, uint32_t N_elems,
+			 int elem_type, const uint32_t *adj, double E, double nu,
+			 double density, int self_weight, double gx, double gy,
+			 int analysis, double thickness, const uint8_t *enabled,
+			 const double *elem_scale,
+			 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
+			 double *F)
 {
 	elem_t el;
 	nbo_elem_tables(elem_type, &el.n, &el.ngp, el.w, el.Ni, el.dpsi,
@@ -127,6 +164,9 @@ int nbo_assemble(uint32_t N_nod, const double *nod, uint32_t N_elems,
 		if (!enabled || enabled[e]) {
 			nbo_constitutive(E, nu, analysis, D);
 			rho = density;
+			if (elem_scale)
+				for (int k = 0; k < 4; k++)
+					D[k] = D[k] * elem_scale[e];
 		}
 		double fx = 0.0, fy = 0.0;
 		if (self_weight) {

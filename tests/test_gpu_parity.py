@@ -364,3 +364,50 @@ def test_fem_driver_bit_identical_in_reference_order(nbgpu_lib, sequential_dots,
     st, rep, disp, strain = run_driver(nbgpu_lib, g)
     assert (rep.iters, rep.status, rep.residual) == (int(g["pcg_iters"]), int(g["pcg_status"]), float(g["pcg_res"]))
     assert np.array_equal(disp, g["x"]) and np.array_equal(strain, g["strain"])
+
+
+# ----------------------------------------------------------------------- session --
+
+def test_fem_session_repeated_assembly_and_warm_start(nbgpu_lib):
+    """BASELINE.json configs[4] at test size: one device-resident session, several steps of
+    {re-assemble with a new element mask / per-element stiffness factors, boundary conditions, warm-started
+    Jacobi-PCG}.  Each step is checked against the oracle run on the same inputs (same x0)."""
+    g = golden("quad_cantilever_64x16")
+    m = mesh_of(g)
+    L = nbgpu_lib
+    p = lambda a, t: a.ctypes.data_as(t)  # noqa: E731
+    d = _Desc(m.n_nod, p(m.nod, capi.f64p), m.n_elems, m.npe, p(m.adj, capi.u32p), m.n_edg, p(m.edg, capi.u32p),
+              m.vtx.size, p(m.vtx, capi.u32p), m.sgm_sizes.size, p(m.sgm_sizes, capi.u32p), p(m.sgm_nodes, capi.u32p))
+    recs = bc_records(g)
+    neu_dof, neu_add, dir_dof, dir_val = flatten_bcs(m, recs)
+    D = api.constitutive_matrix(float(g["E"]), float(g["nu"]), 0)
+    S = C.c_void_p()
+    capi.check(L.nbgpu_fem_session_create(C.byref(d), None, p(D, capi.f64p), 0.0, neu_dof.size, p(neu_dof, capi.u32p),
+                                          p(neu_add, capi.f64p), dir_dof.size, p(dir_dof, capi.u32p),
+                                          p(dir_val, capi.f64p), 0, None, float(g["thickness"]), capi.ASSEMBLY_GATHER,
+                                          C.byref(S)))
+    rng = np.random.default_rng(11)
+    tol = 1e-8 * float(np.linalg.norm(g["F_post"]))
+    steps = [(None, None),
+             ((rng.random(m.n_elems) > 0.15).astype(np.uint8), None),                       # void elements
+             (None, 0.25 + 0.75 * rng.random(m.n_elems) ** 3),                              # SIMP-like factors
+             ((rng.random(m.n_elems) > 0.1).astype(np.uint8), 0.5 + 0.5 * rng.random(m.n_elems))]
+    x_prev = np.zeros(2 * m.n_nod)
+    disp = np.zeros(2 * m.n_nod)
+    for k, (en, sc) in enumerate(steps):
+        rep = _Report()
+        st = L.nbgpu_fem_session_step(S, None if en is None else p(en, capi.u8p), None if sc is None else p(sc, capi.f64p),
+                                      1, 0, tol, C.byref(rep))
+        assert st == 0, L.nbgpu_last_error()
+        capi.check(L.nbgpu_fem_session_results(S, p(disp, capi.f64p), None))
+        K = port.Csr(g["rows_size"], g["cols"])
+        ost, F = port.assemble(K, m, float(g["E"]), float(g["nu"]), thickness=float(g["thickness"]), enabled=en,
+                               elem_scale=sc)
+        port.set_bconditions(m, K, F, recs)
+        ost, ox, oit, ores = K.pcg_jacobi(F, x0=x_prev, tol=tol)          # same warm start as the device
+        assert rep.status == ost == 0 and iters_close(rep.iters, oit), (k, rep.iters, oit)
+        assert rel_l2(disp, ox) <= TOL_VALUES, (k, rel_l2(disp, ox))
+        if k == 0:
+            assert rel_l2(disp, g["x"]) <= 1e-7       # golden solve used the absolute 1e-8
+        x_prev = disp.copy()
+    capi.check(L.nbgpu_fem_session_destroy(S))
