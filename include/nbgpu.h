@@ -230,6 +230,16 @@ int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof,
 int nbgpu_apply_dirichlet(nbgpu_matrix_t *K, double *d_F, uint32_t n,
 			  const uint32_t *dof, const double *value);
 
+/* The same two steps with the lists kept on the device, for loops that re-assemble
+ * and re-apply unchanged boundary conditions (no allocation, no sync per step). */
+typedef struct nbgpu_dirichlet_s nbgpu_dirichlet_t;
+int nbgpu_dirichlet_create(uint32_t N, uint32_t n, const uint32_t *dof,
+			   const double *value, nbgpu_dirichlet_t **out);
+int nbgpu_dirichlet_apply(nbgpu_matrix_t *K, double *d_F, const nbgpu_dirichlet_t *bc);
+int nbgpu_dirichlet_destroy(nbgpu_dirichlet_t *bc);
+int nbgpu_vector_add_entries_dev(double *d_F, uint32_t n, const uint32_t *d_dof,
+				 const double *d_add);
+
 /* pipeline_compute_strain (pipeline.c:266-319): strain[3*N_gp*N_elems] */
 int nbgpu_compute_strain(const nbgpu_mesh_t *mesh,
 			 const nbgpu_elem_tables_t *tables,

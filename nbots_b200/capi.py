@@ -94,6 +94,10 @@ SIGNATURES = {
                                               C.POINTER(AssemblyParams), u8p, f64p, C.c_void_p, u32p]),
     "nbgpu_vector_add_entries": (C.c_int, [C.c_void_p, C.c_uint32, u32p, f64p]),
     "nbgpu_apply_dirichlet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p, f64p]),
+    "nbgpu_dirichlet_create": (C.c_int, [C.c_uint32, C.c_uint32, u32p, f64p, vpp]),
+    "nbgpu_dirichlet_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nbgpu_dirichlet_destroy": (C.c_int, [C.c_void_p]),
+    "nbgpu_vector_add_entries_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "nbgpu_compute_strain": (C.c_int, [C.c_void_p, C.POINTER(ElemTables), C.c_void_p, C.c_void_p]),
     "nbgpu_stress_from_strain": (C.c_int, [C.c_uint32, C.c_uint32, f64p, f64p, u8p, C.c_void_p, C.c_void_p]),
     "nbgpu_fem_session_create": (C.c_int, [C.c_void_p, C.c_void_p, f64p, C.c_double, C.c_uint32, u32p, f64p, C.c_uint32,

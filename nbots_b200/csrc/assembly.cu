@@ -769,15 +769,32 @@ int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof, const
 	return NBGPU_OK;
 }
 
-int nbgpu_apply_dirichlet(nbgpu_matrix_t *K, double *d_F, uint32_t n, const uint32_t *dof,
-			  const double *value)
+/* prepared (device-resident) list of prescribed dofs: built once, applied after every re-assembly */
+struct nbgpu_dirichlet_s {
+	uint32_t N = 0;
+	size_t m = 0;
+	void *buf = nullptr;          // v_first[m] | v_last[m] | order[N]
+	const double *d_first = nullptr, *d_last = nullptr;
+	const uint32_t *d_order = nullptr;
+};
+
+int nbgpu_dirichlet_destroy(nbgpu_dirichlet_t *bc)
+{
+	if (!bc)
+		return NBGPU_OK;
+	if (ctx().ready && bc->buf) {
+		cudaStreamSynchronize(ctx().stream);
+		cudaFree(bc->buf);
+	}
+	delete bc;
+	return NBGPU_OK;
+}
+
+int nbgpu_dirichlet_create(uint32_t N, uint32_t n, const uint32_t *dof, const double *value,
+			   nbgpu_dirichlet_t **out)
 {
 	NB_INIT();
-	if (n == 0)
-		return NBGPU_OK;
-	NB_ARG(K != nullptr && d_F != nullptr && dof != nullptr && value != nullptr);
-	Context &c = ctx();
-	const uint32_t N = K->N;
+	NB_ARG(out != nullptr && (n == 0 || (dof != nullptr && value != nullptr)));
 	// flatten the ordered list: first occurrence decides the elimination order
 	// and the value moved to the right-hand side, the last occurrence decides
 	// F[dof] (see dirichlet_kernel)
@@ -795,29 +812,73 @@ int nbgpu_apply_dirichlet(nbgpu_matrix_t *K, double *d_F, uint32_t n, const uint
 			v_last[order[dof[k]] - 1] = value[k];
 		}
 	}
-	const size_t m = v_first.size();
-	void *buf = nullptr;
-	NB_CUDA(cudaMalloc(&buf, (size_t)N * sizeof(uint32_t) + 2 * m * sizeof(double) + 16));
-	double *d_first = (double *)buf, *d_last = d_first + m;
+	nbgpu_dirichlet_t *bc = new nbgpu_dirichlet_t();
+	bc->N = N;
+	bc->m = v_first.size();
+	const size_t m = bc->m;
+	cudaError_t e = cudaMalloc(&bc->buf, (size_t)N * sizeof(uint32_t) + 2 * m * sizeof(double) + 16);
+	double *d_first = (double *)bc->buf, *d_last = d_first + m;
 	uint32_t *d_order = (uint32_t *)(d_last + m);
-	cudaError_t e = cudaMemcpy(d_first, v_first.data(), m * sizeof(double), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(d_first, v_first.data(), m * sizeof(double), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(d_last, v_last.data(), m * sizeof(double), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(d_order, order.data(), (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) {
-		dirichlet_kernel<<<(N + kBlock - 1) / kBlock, kBlock, 0, c.stream>>>(
-			N, K->d_slice_off, K->d_col, K->d_val, d_F, d_order, d_first, d_last);
-		ctx().launches++;
-		e = cudaGetLastError();
-	}
-	if (e == cudaSuccess)
-		e = cudaStreamSynchronize(c.stream);
-	cudaFree(buf);
 	if (e != cudaSuccess) {
-		set_error("apply_dirichlet: %s", cudaGetErrorString(e));
+		set_error("dirichlet_create: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		bc->buf = e == cudaErrorMemoryAllocation ? nullptr : bc->buf;
+		nbgpu_dirichlet_destroy(bc);
 		return NBGPU_ERR_CUDA;
 	}
+	bc->d_first = d_first;
+	bc->d_last = d_last;
+	bc->d_order = d_order;
+	*out = bc;
+	return NBGPU_OK;
+}
+
+/* stream-ordered; does not synchronise */
+int nbgpu_dirichlet_apply(nbgpu_matrix_t *K, double *d_F, const nbgpu_dirichlet_t *bc)
+{
+	NB_INIT();
+	NB_ARG(K != nullptr && d_F != nullptr && bc != nullptr && bc->N == K->N);
+	if (bc->m == 0)
+		return NBGPU_OK;
+	dirichlet_kernel<<<(K->N + kBlock - 1) / kBlock, kBlock, 0, ctx().stream>>>(
+		K->N, K->d_slice_off, K->d_col, K->d_val, d_F, bc->d_order, bc->d_first, bc->d_last);
+	NB_LAUNCHED();
+	return NBGPU_OK;
+}
+
+int nbgpu_apply_dirichlet(nbgpu_matrix_t *K, double *d_F, uint32_t n, const uint32_t *dof,
+			  const double *value)
+{
+	NB_INIT();
+	if (n == 0)
+		return NBGPU_OK;
+	NB_ARG(K != nullptr && d_F != nullptr && dof != nullptr && value != nullptr);
+	nbgpu_dirichlet_t *bc = nullptr;
+	NB_TRY(nbgpu_dirichlet_create(K->N, n, dof, value, &bc));
+	int st = nbgpu_dirichlet_apply(K, d_F, bc);
+	if (st == NBGPU_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) {
+		set_error("apply_dirichlet: %s", cudaGetErrorString(cudaGetLastError()));
+		st = NBGPU_ERR_CUDA;
+	}
+	nbgpu_dirichlet_destroy(bc);
+	return st;
+}
+
+/* F[d_dof[k]] += d_add[k] with the lists already on the device; stream-ordered */
+int nbgpu_vector_add_entries_dev(double *d_F, uint32_t n, const uint32_t *d_dof, const double *d_add)
+{
+	NB_INIT();
+	if (n == 0)
+		return NBGPU_OK;
+	NB_ARG(d_F != nullptr && d_dof != nullptr && d_add != nullptr);
+	vector_add_entries_kernel<<<1, 32, 0, ctx().stream>>>(d_F, n, d_dof, d_add);
+	NB_LAUNCHED();
 	return NBGPU_OK;
 }
 

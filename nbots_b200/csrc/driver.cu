@@ -186,8 +186,10 @@ struct nbgpu_fem_session_s {
 	double *d_vec = nullptr, *d_F = nullptr, *d_x = nullptr, *d_strain = nullptr;
 	nbgpu_elem_tables_t tables;
 	nbgpu_assembly_params_t ap;
-	std::vector<uint32_t> neu_dof, dir_dof;
-	std::vector<double> neu_add, dir_val;
+	uint32_t n_neu = 0;
+	uint32_t *d_neu_dof = nullptr;        // boundary-condition lists, resident on the device
+	double *d_neu_add = nullptr;
+	nbgpu_dirichlet_t *dirichlet = nullptr;
 	double ms_pattern = 0, ms_upload = 0;
 	bool have_x = false;
 };
@@ -197,6 +199,8 @@ int nbgpu_fem_session_destroy(nbgpu_fem_session_t *S)
 	if (!S)
 		return NBGPU_OK;
 	nbgpu_free(S->d_vec);
+	nbgpu_free(S->d_neu_add);
+	nbgpu_dirichlet_destroy(S->dirichlet);
 	nbgpu_mesh_destroy(S->mesh);
 	nbgpu_matrix_destroy(S->K);
 	delete S;
@@ -234,10 +238,7 @@ int nbgpu_fem_session_create(const nbgpu_mesh_desc_t *md, const nbgpu_elem_table
 		S->ap.gravity[1] = gravity[1];
 	}
 	S->ap.mode = assembly_mode;
-	S->neu_dof.assign(neu_dof, neu_dof + n_neu);
-	S->neu_add.assign(neu_add, neu_add + n_neu);
-	S->dir_dof.assign(dir_dof, dir_dof + n_dir);
-	S->dir_val.assign(dir_val, dir_val + n_dir);
+	S->n_neu = n_neu;
 
 	// (1) graph + sparsity pattern (static_elasticity2D.c:45-50)
 	double t0 = now_ms();
@@ -261,6 +262,17 @@ int nbgpu_fem_session_create(const nbgpu_mesh_desc_t *md, const nbgpu_elem_table
 		st = nbgpu_mesh_create(md->N_nod, md->nod, md->N_elems, md->nodes_per_elem, md->adj, &S->mesh);
 	if (st == NBGPU_OK)
 		st = nbgpu_malloc((void **)&S->d_vec, (2 * (size_t)S->N + n_strain) * sizeof(double));
+	if (st == NBGPU_OK && n_neu) {
+		st = nbgpu_malloc((void **)&S->d_neu_add, (size_t)n_neu * (sizeof(double) + sizeof(uint32_t)));
+		if (st == NBGPU_OK) {
+			S->d_neu_dof = (uint32_t *)(S->d_neu_add + n_neu);
+			st = nbgpu_copy_h2d(S->d_neu_add, neu_add, (size_t)n_neu * sizeof(double));
+		}
+		if (st == NBGPU_OK)
+			st = nbgpu_copy_h2d(S->d_neu_dof, neu_dof, (size_t)n_neu * sizeof(uint32_t));
+	}
+	if (st == NBGPU_OK)
+		st = nbgpu_dirichlet_create(S->N, n_dir, dir_dof, dir_val, &S->dirichlet);
 	if (st == NBGPU_OK) {
 		S->d_F = S->d_vec;
 		S->d_x = S->d_vec + S->N;
@@ -301,10 +313,11 @@ int nbgpu_fem_session_step(nbgpu_fem_session_t *S, const uint8_t *enabled, const
 	// (4) boundary conditions (static_elasticity2D.c:67)
 	if (st == NBGPU_OK && status == 0) {
 		t0 = now_ms();
-		st = nbgpu_vector_add_entries(S->d_F, (uint32_t)S->neu_dof.size(), S->neu_dof.data(), S->neu_add.data());
+		st = nbgpu_vector_add_entries_dev(S->d_F, S->n_neu, S->d_neu_dof, S->d_neu_add);
 		if (st == NBGPU_OK)
-			st = nbgpu_apply_dirichlet(S->K, S->d_F, (uint32_t)S->dir_dof.size(), S->dir_dof.data(),
-						   S->dir_val.data());
+			st = nbgpu_dirichlet_apply(S->K, S->d_F, S->dirichlet);
+		if (st == NBGPU_OK)
+			st = nbgpu_sync();
 		rep.ms_bcond = now_ms() - t0;
 	}
 	// (5) solver(): x0 = 0 (or the previous displacement), abs tol; 0 and 1 both accepted (:83-97)
