@@ -46,6 +46,14 @@ def workload_mesh(n_gpus):
     return meshgen.structured_mesh(nx, ny, 2.0, 1.0 * n_gpus, kind=1)
 
 
+def workload_name(n_gpus):
+    if n_gpus == 1:
+        return ("Q1: structured-quad cantilever 1000x500, plane stress, Jacobi-PCG to 1e-8*|b| "
+                "(BASELINE.json configs[1])")
+    return (f"Q1 x {n_gpus}: structured-quad cantilever {NX}x{NY_PER_GPU * n_gpus} in {n_gpus} slabs of grid lines, "
+            "plane stress, Jacobi-PCG to 1e-8*|b| (BASELINE.json configs[1] per GPU)")
+
+
 def workload_bcs():
     # clamp side x=0 (segment 3), total traction (0,-1) on side x=L (segment 1)
     return [("dirichlet", "sgm", 3, (1, 1), (0.0, 0.0)), ("neumann", "sgm", 1, (1, 1), (0.0, -1.0))]
@@ -245,8 +253,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Q1: structured-quad cantilever 1000x500, plane stress, Jacobi-PCG to 1e-8*|b| "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": workload_name(1),
                        "N_dof": N, "nnz": int(nnz), "iterations_per_step": int(iters), "rel_tol": REL_TOL,
                        "l2": "working set 265 MB (matrix 216 MB + 6 vectors) exceeds the 126 MB L2; no flush",
                        "assembly_ms_on_device": round(ms_assembly, 3), "setup_s": round(t_setup, 2)},
@@ -320,8 +327,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(tot_t / args.steps * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Q1 x {args.gpus}: structured-quad cantilever {NX}x{NY_PER_GPU * args.gpus}, "
-                                   "plane stress, Jacobi-PCG (BASELINE.json configs[1])", "N_dof": int(N)},
+            "config": {"workload": workload_name(args.gpus), "N_dof": int(N),
+                       "sample": "fixed iteration budget per step from x0 = 0 (a full CPU solve takes minutes)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{tot_it // args.steps} PCG iterations per step from x0=0, "
                                        f"nb_sparse_solve_CG_precond_Jacobi with omp_parallel_threads={cores}"},

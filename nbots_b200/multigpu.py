@@ -293,8 +293,7 @@ def bench(args, rank, world, dist):
         line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"Q1 x {world}: structured-quad cantilever {nx}x{ny} in {world} slabs of grid "
-                                       "lines, plane stress, Jacobi-PCG to 1e-8*|b| (BASELINE.json configs[1] per GPU)",
+                "config": {"workload": B.workload_name(world),
                            "N_dof": int(N_global), "nnz": int(nnz_global), "iterations_per_step": int(iters),
                            "rel_tol": B.REL_TOL, "dof_per_gpu": int(N_loc), "halo_values_per_rank": int(dc.n_halo),
                            "exchange": "NVLink peer stores + sequence flags (CUDA IPC windows); no NCCL in the loop",

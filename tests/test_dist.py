@@ -25,7 +25,7 @@ def test_partition_plan_and_exchange_on_cpu(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 3])
 def test_distributed_solve_on_gpus(nbgpu_lib, world):
     """One rank per GPU when the box has several; on a single-GPU box both ranks share GPU 0 (CUDA IPC works
     within one device; the kernels of the two processes are time-sliced, so this only checks correctness)."""
