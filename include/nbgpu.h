@@ -95,6 +95,12 @@ int nbgpu_matrix_destroy(nbgpu_matrix_t *A);
 /* N, nnz, slices, stored (padded) entries */
 int nbgpu_matrix_info(const nbgpu_matrix_t *A, uint32_t *N, uint64_t *nnz,
 		      uint32_t *n_slices, uint64_t *stored_entries);
+/* how the rows are stored: sigma = sorting window of the SELL-32-sigma layout
+ * (1 = rows in natural order), uniform_width != 0 when every slice has that
+ * width, blocked != 0 when the 2x2 node-block column ids are in use */
+int nbgpu_matrix_layout(const nbgpu_matrix_t *A, uint32_t *sigma,
+			uint32_t *uniform_width, uint32_t *max_width,
+			int *blocked);
 int nbgpu_matrix_set_values_rows(nbgpu_matrix_t *A, double *const *rows_values);
 int nbgpu_matrix_set_values_csr(nbgpu_matrix_t *A, const double *vals);
 int nbgpu_matrix_get_values_rows(const nbgpu_matrix_t *A, double *const *rows_values);

@@ -129,15 +129,20 @@ __global__ void __launch_bounds__(kBlock)
 assemble_gather_kernel(uint32_t N_nod, const double *__restrict__ nod, const uint32_t *__restrict__ adj,
 		       const uint32_t *__restrict__ n2e_ptr, const uint32_t *__restrict__ n2e,
 		       const uint8_t *__restrict__ enabled, const double *__restrict__ scale, AsmParams P,
-		       const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ col,
-		       double *__restrict__ val, double *__restrict__ F, unsigned int *first_bad,
-		       int *pattern_miss)
+		       const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ perm,
+		       const uint32_t *__restrict__ col, double *__restrict__ val, double *__restrict__ F,
+		       unsigned int *first_bad, int *pattern_miss)
 {
-	const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+	// thread = storage position (slice * 32 + lane), so that the value stores stay coalesced
+	// whatever the row order of the layout is
+	const uint32_t spos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (spos >= ((2 * N_nod + kSliceRows - 1) / kSliceRows) * kSliceRows)
+		return;
+	const uint32_t row = perm ? perm[spos] : spos;
 	if (row >= 2 * N_nod)
 		return;
-	const uint32_t node = row >> 1, a = row & 1, lane = row & 31;
-	const uint32_t off = slice_off[row >> 5], width = slice_off[(row >> 5) + 1] - off;
+	const uint32_t node = row >> 1, a = row & 1, lane = spos & 31;
+	const uint32_t off = slice_off[spos >> 5], width = slice_off[(spos >> 5) + 1] - off;
 	double f_acc = 0.0;
 	for (uint32_t t = n2e_ptr[node]; t < n2e_ptr[node + 1]; t++) {
 		const uint32_t e = n2e[t];
@@ -223,9 +228,9 @@ __global__ void __launch_bounds__(128)
 assemble_element_kernel(uint32_t n_work, const uint32_t *__restrict__ work /* null = identity */,
 			const double *__restrict__ nod, const uint32_t *__restrict__ adj,
 			const uint8_t *__restrict__ enabled, const double *__restrict__ scale, AsmParams P,
-			const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ col,
-			double *__restrict__ val, double *__restrict__ F, unsigned int *first_bad,
-			int *pattern_miss)
+			const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ inv_perm,
+			const uint32_t *__restrict__ col, double *__restrict__ val, double *__restrict__ F,
+			unsigned int *first_bad, int *pattern_miss)
 {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_work)
@@ -284,12 +289,13 @@ assemble_element_kernel(uint32_t n_work, const uint32_t *__restrict__ work /* nu
 #pragma unroll
 		for (int a = 0; a < 2; a++) {
 			const uint32_t row = 2 * v[i] + a;
-			const uint32_t off = slice_off[row >> 5], width = slice_off[(row >> 5) + 1] - off;
+			const uint32_t spos = inv_perm ? inv_perm[row] : row;
+			const uint32_t off = slice_off[spos >> 5], width = slice_off[(spos >> 5) + 1] - off;
 #pragma unroll
 			for (int j = 0; j < NPE; j++) {
 #pragma unroll
 				for (int b = 0; b < 2; b++) {
-					const size_t pos = find_in_row(col, off, width, row & 31, 2 * v[j] + b);
+					const size_t pos = find_in_row(col, off, width, spos & 31, 2 * v[j] + b);
 					if (pos == (size_t)-1) {
 						*pattern_miss = 1;
 						continue;
@@ -332,15 +338,19 @@ __global__ void vector_add_entries_kernel(double *F, uint32_t n, const uint32_t 
 //                       F[i] -= A_ic * v_first[c], subtracted in the order the
 //                       constraints were applied (ascending order[c]).
 __global__ void __launch_bounds__(kBlock)
-dirichlet_kernel(uint32_t N, const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ col,
+dirichlet_kernel(uint32_t N, uint32_t n_pos, const uint32_t *__restrict__ slice_off,
+		 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ col,
 		 double *__restrict__ val, double *__restrict__ F, const uint32_t *__restrict__ order,
 		 const double *__restrict__ v_first, const double *__restrict__ v_last)
 {
-	const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t spos = blockIdx.x * blockDim.x + threadIdx.x;   // storage position
+	if (spos >= n_pos)
+		return;
+	const uint32_t row = perm ? perm[spos] : spos;
 	if (row >= N)
 		return;
-	const uint32_t lane = row & 31;
-	const uint32_t off = slice_off[row >> 5], width = slice_off[(row >> 5) + 1] - off;
+	const uint32_t lane = spos & 31;
+	const uint32_t off = slice_off[spos >> 5], width = slice_off[(spos >> 5) + 1] - off;
 	const uint32_t *cp = col + (size_t)off * kSliceRows + lane;
 	double *vp = val + (size_t)off * kSliceRows + lane;
 	const uint32_t my = order[row];
@@ -502,16 +512,16 @@ int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int 
 {
 	Context &c = ctx();
 	if (mode == NBGPU_ASSEMBLY_GATHER) {
-		const uint32_t rows = 2 * m->N_nod;
+		const uint32_t rows = K->n_slices * kSliceRows;
 		assemble_gather_kernel<NPE, NGP><<<(rows + kBlock - 1) / kBlock, kBlock, 0, c.stream>>>(
 			m->N_nod, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, P, K->d_slice_off,
-			K->d_col, K->d_val, d_F, d_bad, d_miss);
+			K->d_perm, K->d_col, K->d_val, d_F, d_bad, d_miss);
 		NB_LAUNCHED();
 	} else if (mode == NBGPU_ASSEMBLY_ATOMIC) {
 		NB_CUDA(cudaMemsetAsync(d_F, 0, 2 * (size_t)m->N_nod * sizeof(double), c.stream));
 		assemble_element_kernel<NPE, NGP, true><<<(m->N_elems + 127) / 128, 128, 0, c.stream>>>(
-			m->N_elems, nullptr, m->d_nod, m->d_adj, d_en, d_scale, P, K->d_slice_off, K->d_col,
-			K->d_val, d_F, d_bad, d_miss);
+			m->N_elems, nullptr, m->d_nod, m->d_adj, d_en, d_scale, P, K->d_slice_off, K->d_inv_perm,
+			K->d_col, K->d_val, d_F, d_bad, d_miss);
 		NB_LAUNCHED();
 	} else {
 		NB_TRY(build_coloring(m));
@@ -522,7 +532,7 @@ int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int 
 				continue;
 			assemble_element_kernel<NPE, NGP, false><<<(n + 127) / 128, 128, 0, c.stream>>>(
 				n, m->d_color_elems + m->color_ptr[col], m->d_nod, m->d_adj, d_en, d_scale, P,
-				K->d_slice_off, K->d_col, K->d_val, d_F, d_bad, d_miss);
+				K->d_slice_off, K->d_inv_perm, K->d_col, K->d_val, d_F, d_bad, d_miss);
 			NB_LAUNCHED();
 		}
 	}
@@ -846,8 +856,9 @@ int nbgpu_dirichlet_apply(nbgpu_matrix_t *K, double *d_F, const nbgpu_dirichlet_
 	NB_ARG(K != nullptr && d_F != nullptr && bc != nullptr && bc->N == K->N);
 	if (bc->m == 0)
 		return NBGPU_OK;
-	dirichlet_kernel<<<(K->N + kBlock - 1) / kBlock, kBlock, 0, ctx().stream>>>(
-		K->N, K->d_slice_off, K->d_col, K->d_val, d_F, bc->d_order, bc->d_first, bc->d_last);
+	const uint32_t n_pos = K->n_slices * kSliceRows;
+	dirichlet_kernel<<<(n_pos + kBlock - 1) / kBlock, kBlock, 0, ctx().stream>>>(
+		K->N, n_pos, K->d_slice_off, K->d_perm, K->d_col, K->d_val, d_F, bc->d_order, bc->d_first, bc->d_last);
 	NB_LAUNCHED();
 	return NBGPU_OK;
 }

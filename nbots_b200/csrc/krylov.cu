@@ -133,7 +133,7 @@ __device__ __forceinline__ void spmv_finish(double (&dots)[1], double *partials,
 template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock, 4)
 krylov_init_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
-		   const double *__restrict__ val, const uint32_t *__restrict__ col,
+		   const uint32_t *__restrict__ perm, const double *__restrict__ val, const uint32_t *__restrict__ col,
 		   const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ g,
 		   double *__restrict__ p, double *__restrict__ q, double *__restrict__ diag,
 		   double *partials, KrylovState *st)
@@ -144,12 +144,12 @@ krylov_init_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ s
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	double dots[2] = {0.0, 0.0};
 	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
-		const uint32_t row = s * kSliceRows + lane;
+		const uint32_t row = perm ? __ldg(perm + (size_t)s * kSliceRows + lane) : s * kSliceRows + lane;
 		const uint32_t off = __ldg(slice_off + s);
 		const uint32_t width = __ldg(slice_off + s + 1) - off;
 		double d = 0.0;
 		const double acc = sell_row_times<kIterUnroll, JACOBI>(val, col, off, width, lane, row,
-								       min(row, N - 1), x, &d);
+								       0u, x, &d);
 		if (row < N)
 			init_row<JACOBI>(row, acc, d, b, g, p, q, diag, dots);
 	}
@@ -158,7 +158,7 @@ krylov_init_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ s
 
 __global__ void __launch_bounds__(kBlock, 4)
 krylov_spmv_kernel(uint32_t k, uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
-		   const double *__restrict__ val, const uint32_t *__restrict__ col,
+		   const uint32_t *__restrict__ perm, const double *__restrict__ val, const uint32_t *__restrict__ col,
 		   const double *__restrict__ p, double *__restrict__ w, double *partials,
 		   KrylovState *st)
 {
@@ -170,11 +170,11 @@ krylov_spmv_kernel(uint32_t k, uint32_t N, uint32_t n_slices, const uint32_t *__
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	double dots[1] = {0.0};
 	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
-		const uint32_t row = s * kSliceRows + lane;
+		const uint32_t row = perm ? __ldg(perm + (size_t)s * kSliceRows + lane) : s * kSliceRows + lane;
 		const uint32_t off = __ldg(slice_off + s);
 		const uint32_t width = __ldg(slice_off + s + 1) - off;
 		const double acc = sell_row_times<kIterUnroll, false>(val, col, off, width, lane, row,
-								      min(row, N - 1), p, nullptr);
+								      0u, p, nullptr);
 		if (row < N) {
 			w[row] = acc;
 			dots[0] = __dadd_rn(dots[0], __dmul_rn(__ldg(p + row), acc));
@@ -494,6 +494,7 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 	V.N = N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
 	V.col = A->blocked ? A->d_bcol : A->d_col;
 	V.uniform_width = A->uniform_width;
+	V.perm = A->d_perm;
 	StreamConfig scfg, icfg;
 	const void *sk = A->blocked ? (const void *)krylov_spmv_stream_kernel<true>
 				    : (const void *)krylov_spmv_stream_kernel<false>;
@@ -521,10 +522,10 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 			e = launch(false, krylov_init_stream_kernel<false, false>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
 				   xw, g, p, q, diag, partials, st);
 	} else if (jacobi) {
-		e = launch(false, krylov_init_kernel<true>, igrid, 0, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col,
+		e = launch(false, krylov_init_kernel<true>, igrid, 0, N, A->n_slices, A->d_slice_off, A->d_perm, A->d_val, A->d_col,
 			   d_b, xw, g, p, q, diag, partials, st);
 	} else {
-		e = launch(false, krylov_init_kernel<false>, igrid, 0, N, A->n_slices, A->d_slice_off, A->d_val, A->d_col,
+		e = launch(false, krylov_init_kernel<false>, igrid, 0, N, A->n_slices, A->d_slice_off, A->d_perm, A->d_val, A->d_col,
 			   d_b, xw, g, p, q, diag, partials, st);
 	}
 	NB_CUDA(e);
@@ -556,7 +557,7 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 				e = launch(pdl, krylov_spmv_stream_kernel<false>, scfg.grid, scfg.smem_bytes, k, V, scfg, p, w,
 					   partials, st);
 			else
-				e = launch(pdl, krylov_spmv_kernel, sgrid, 0, k, N, A->n_slices, A->d_slice_off, A->d_val,
+				e = launch(pdl, krylov_spmv_kernel, sgrid, 0, k, N, A->n_slices, A->d_slice_off, A->d_perm, A->d_val,
 					   A->d_col, p, w, partials, st);
 			NB_CUDA(e);
 			if (seq) {
@@ -585,7 +586,7 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 		}
 		if (k == max_iter) {
 			// the loop test that ends the reference's while at k == max_iter
-			NB_CUDA(launch(false, krylov_spmv_kernel, 1, 0, k, N, A->n_slices, A->d_slice_off, A->d_val,
+			NB_CUDA(launch(false, krylov_spmv_kernel, 1, 0, k, N, A->n_slices, A->d_slice_off, A->d_perm, A->d_val,
 				       A->d_col, p, w, partials, st));
 		}
 		NB_CUDA(cudaMemcpyAsync(&hst[slot], st, sizeof(KrylovState), cudaMemcpyDeviceToHost, c.stream));

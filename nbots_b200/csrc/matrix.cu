@@ -20,13 +20,13 @@ constexpr size_t kStageBytes = size_t(32) << 20;   // per pinned staging buffer
 __global__ void __launch_bounds__(kBlock)
 csr_to_sell_kernel(uint32_t N, uint32_t n_cols, bool sorted, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
 		   const uint32_t *__restrict__ csr_col, const double *__restrict__ csr_val,
-		   const uint32_t *__restrict__ slice_off, uint32_t *__restrict__ sell_col,
-		   double *__restrict__ sell_val, int *bad)
+		   const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ perm,
+		   uint32_t *__restrict__ sell_col, double *__restrict__ sell_val, int *bad)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
-		const uint32_t row = s * kSliceRows + lane;
+		const uint32_t row = perm ? perm[s * kSliceRows + lane] : s * kSliceRows + lane;
 		const uint32_t off = slice_off[s], width = slice_off[s + 1] - off;
 		uint64_t base = 0;
 		uint32_t len = 0;
@@ -100,14 +100,14 @@ build_bcol_kernel(uint32_t n_slices, const uint32_t *__restrict__ slice_off,
 
 __global__ void __launch_bounds__(kBlock)
 sell_to_csr_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
-		   const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ sell_col,
-		   const double *__restrict__ sell_val, uint32_t *__restrict__ csr_col,
-		   double *__restrict__ csr_val)
+		   const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ perm,
+		   const uint32_t *__restrict__ sell_col, const double *__restrict__ sell_val,
+		   uint32_t *__restrict__ csr_col, double *__restrict__ csr_val)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
-		const uint32_t row = s * kSliceRows + lane;
+		const uint32_t row = perm ? perm[s * kSliceRows + lane] : s * kSliceRows + lane;
 		if (row >= N)
 			continue;
 		const uint32_t off = slice_off[s];
@@ -248,16 +248,68 @@ int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
 	A->nnz = A->h_row_ptr[N];
 	A->n_slices = (N + kSliceRows - 1) / kSliceRows;
 	std::vector<uint32_t> off((size_t)A->n_slices + 1), width((size_t)A->n_slices);
+	const size_t n_pos = (size_t)A->n_slices * kSliceRows;
+	auto slice_widths = [&](const uint32_t *perm, uint64_t *units_out) {
+		uint64_t units = 0;
+		uint32_t wmax = 0;
+		for (uint32_t s = 0; s < A->n_slices; s++) {
+			uint32_t w = 0;
+			for (uint32_t l = 0; l < kSliceRows; l++) {
+				const size_t pos = (size_t)s * kSliceRows + l;
+				const uint32_t r = perm ? perm[pos] : (uint32_t)pos;
+				if (pos < n_pos && r < N)
+					w = std::max(w, rows_size[r]);
+			}
+			width[s] = w;
+			wmax = std::max(wmax, w);
+			units += w;
+		}
+		A->max_width = wmax;
+		*units_out = units;
+	};
 	uint64_t units = 0;
-	A->max_width = 0;
-	for (uint32_t s = 0; s < A->n_slices; s++) {
-		uint32_t w = 0;
-		const uint32_t r1 = std::min<uint64_t>(N, (uint64_t)(s + 1) * kSliceRows);
-		for (uint32_t r = s * kSliceRows; r < r1; r++)
-			w = std::max(w, rows_size[r]);
-		width[s] = w;
-		A->max_width = std::max(A->max_width, w);
-		units += w;
+	slice_widths(nullptr, &units);
+	// SELL-C-sigma: worth it when the identity order pads more than 5 % (irregular meshes).
+	// Rank-local blocks keep the identity order (their visit order is planned on plain row ids).
+	A->sigma = 1;
+	{
+		const char *env = getenv("NBGPU_SIGMA");
+		uint32_t want = env ? (uint32_t)atoi(env) : 0;
+		if (!env && !A->local_block && A->nnz > 0 && units * kSliceRows > A->nnz + A->nnz / 20)
+			want = 256;
+		want = (want / kSliceRows) * kSliceRows;
+		if (want > kSliceRows - 1 && !A->local_block && N > 1)
+			A->sigma = want;
+	}
+	std::vector<uint32_t> perm;
+	if (A->sigma > 1) {
+		perm.assign(n_pos, 0xFFFFFFFFu);
+		bool pairs = (N % 2) == 0;
+		for (uint32_t i = 0; pairs && i + 1 < N; i += 2)
+			pairs = rows_size[i] == rows_size[i + 1];
+		const uint32_t unit = pairs ? 2 : 1;
+		std::vector<uint32_t> ids;
+		for (uint32_t w0 = 0; w0 < N; w0 += A->sigma) {
+			const uint32_t w1 = (uint32_t)std::min<uint64_t>(N, (uint64_t)w0 + A->sigma);
+			ids.clear();
+			for (uint32_t r = w0; r < w1; r += unit)
+				ids.push_back(r);
+			std::stable_sort(ids.begin(), ids.end(),
+					 [&](uint32_t a, uint32_t b) { return rows_size[a] > rows_size[b]; });
+			uint32_t pos = w0;
+			for (uint32_t r : ids)
+				for (uint32_t u = 0; u < unit && r + u < w1; u++)
+					perm[pos++] = r + u;
+		}
+		uint64_t sorted_units = 0;
+		slice_widths(perm.data(), &sorted_units);
+		if (sorted_units >= units) {   // nothing gained: stay with the identity
+			A->sigma = 1;
+			perm.clear();
+			slice_widths(nullptr, &units);
+		} else {
+			units = sorted_units;
+		}
 	}
 	// near-uniform rows (structured meshes): store every slice max_width wide
 	const uint64_t uniform_units = (uint64_t)A->n_slices * A->max_width;
@@ -280,6 +332,16 @@ int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
 	NB_CUDA(cudaMalloc(&A->d_slice_off, off.size() * sizeof(uint32_t)));
 	NB_CUDA(cudaMemcpyAsync(A->d_slice_off, off.data(), off.size() * sizeof(uint32_t),
 				cudaMemcpyHostToDevice, ctx().stream));
+	if (A->sigma > 1) {
+		std::vector<uint32_t> inv(N);
+		for (size_t pos = 0; pos < n_pos; pos++)
+			if (perm[pos] < N)
+				inv[perm[pos]] = (uint32_t)pos;
+		NB_CUDA(cudaMalloc(&A->d_perm, n_pos * sizeof(uint32_t)));
+		NB_CUDA(cudaMalloc(&A->d_inv_perm, (size_t)N * sizeof(uint32_t)));
+		NB_CUDA(cudaMemcpy(A->d_perm, perm.data(), n_pos * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		NB_CUDA(cudaMemcpy(A->d_inv_perm, inv.data(), (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
 	NB_CUDA(cudaStreamSynchronize(ctx().stream));   // `off` goes out of scope
 	cudaError_t e = cudaMalloc(&A->d_val, std::max<size_t>(1, A->stored) * sizeof(double));
 	if (e == cudaSuccess)
@@ -309,7 +371,7 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 	if (A->n_slices) {
 		csr_to_sell_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
 			A->N, A->n_cols, !A->local_block, A->n_slices, (const uint64_t *)rp.p, d_cols, d_vals, A->d_slice_off,
-			d_cols ? A->d_col : nullptr, A->d_val, (int *)bad.p);
+			A->d_perm, d_cols ? A->d_col : nullptr, A->d_val, (int *)bad.p);
 		NB_LAUNCHED();
 	}
 	int h_bad = 0;
@@ -347,7 +409,7 @@ int convert_out(const nbgpu_matrix_t *A, uint32_t *d_cols, double *d_vals)
 				cudaMemcpyHostToDevice, c.stream));
 	if (A->n_slices) {
 		sell_to_csr_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
-			A->N, A->n_slices, (const uint64_t *)rp.p, A->d_slice_off, A->d_col, A->d_val,
+			A->N, A->n_slices, (const uint64_t *)rp.p, A->d_slice_off, A->d_perm, A->d_col, A->d_val,
 			d_cols, d_vals);
 		NB_LAUNCHED();
 	}
@@ -370,6 +432,8 @@ int nbgpu_matrix_destroy(nbgpu_matrix_t *A)
 		cudaFree(A->d_val);
 		cudaFree(A->d_col);
 		cudaFree(A->d_bcol);
+		cudaFree(A->d_perm);
+		cudaFree(A->d_inv_perm);
 	}
 	delete A;
 	return NBGPU_OK;
@@ -467,6 +531,21 @@ int nbgpu_matrix_info(const nbgpu_matrix_t *A, uint32_t *N, uint64_t *nnz, uint3
 		*n_slices = A->n_slices;
 	if (stored_entries)
 		*stored_entries = A->stored;
+	return NBGPU_OK;
+}
+
+int nbgpu_matrix_layout(const nbgpu_matrix_t *A, uint32_t *sigma, uint32_t *uniform_width,
+			uint32_t *max_width, int *blocked)
+{
+	NB_ARG(A != nullptr);
+	if (sigma)
+		*sigma = A->sigma;
+	if (uniform_width)
+		*uniform_width = A->uniform_width;
+	if (max_width)
+		*max_width = A->max_width;
+	if (blocked)
+		*blocked = A->blocked ? 1 : 0;
 	return NBGPU_OK;
 }
 

@@ -34,6 +34,14 @@ struct nbgpu_matrix_s {
 	// block jb of the node pair nl of slice s sits at (slice_off[s]/2 + jb) * 16 + nl.
 	bool blocked = false;
 	uint32_t *d_bcol = nullptr;           // [stored / 4]
+	// SELL-C-sigma: inside windows of `sigma` consecutive rows the rows (row PAIRS when the two
+	// dofs of a node always have equal length, so that the block structure survives) are stored in
+	// order of descending length, which removes most of the padding of irregular (triangle-mesh)
+	// patterns.  d_perm[position] = row (0xFFFFFFFF past the last row), d_inv_perm[row] = position,
+	// position = slice * 32 + lane.  Both null when the order is the identity (sigma == 1).
+	uint32_t sigma = 1;
+	uint32_t *d_perm = nullptr;           // [n_slices * 32]
+	uint32_t *d_inv_perm = nullptr;       // [N]
 	std::vector<uint32_t> h_rows_size;    // host copy of the pattern's row lengths
 	std::vector<uint64_t> h_row_ptr;      // CSR offsets (host), for value import/export
 };

@@ -115,6 +115,7 @@ struct SellView {
 	uint32_t visit_shift = 0;
 	uint32_t late_from = 0xFFFFFFFFu;
 	uint32_t uniform_width = 0;   // != 0: slice s starts at s * uniform_width (no offset loads)
+	const uint32_t *perm = nullptr;   // SELL-C-sigma: row stored at position slice * 32 + lane (null: identity)
 };
 
 // Runs `body(row, acc, diag, x_row)` for every row of the slices this warp owns
@@ -201,10 +202,20 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 
 	uint32_t n = 0;
 	bool late_done = false;
+	// SELL-C-sigma: the row stored at this lane's position is fetched one slice ahead, so that the
+	// load's latency never sits in front of the gathers
+	auto slice_of = [&](uint64_t v) {
+		uint32_t s = (uint32_t)v + A.visit_shift;
+		return s >= A.n_slices ? s - A.n_slices : s;
+	};
+	uint32_t row_ahead = 0;
+	if (A.perm && first < A.n_slices)
+		row_ahead = __ldg(A.perm + (size_t)slice_of(first) * kSliceRows + lane);
 	for (uint64_t s64 = first; s64 < A.n_slices; s64 += total_warps, n++) {
-		uint32_t s = (uint32_t)s64 + A.visit_shift;
-		if (s >= A.n_slices)
-			s -= A.n_slices;
+		const uint32_t s = slice_of(s64);
+		const uint32_t row = A.perm ? row_ahead : s * kSliceRows + lane;
+		if (A.perm && s64 + total_warps < A.n_slices)
+			row_ahead = __ldg(A.perm + (size_t)slice_of(s64 + total_warps) * kSliceRows + lane);
 		const uint32_t st = n % cfg.stages, parity = (n / cfg.stages) & 1u;
 		if (!late_done && s64 >= A.late_from) {
 			late_done = true;
@@ -221,8 +232,6 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		const uint32_t width = m.y;
 		const unsigned char *stage = ring + (size_t)st * cfg.stage_bytes;
 		const double *sval = reinterpret_cast<const double *>(stage) + lane;
-		const uint32_t row = s * kSliceRows + lane;
-		const uint32_t safe = min(row, A.N - 1);
 		double acc = 0.0, diag = 0.0, x_row = 0.0;
 		bool have_row = false;
 		if (!BLOCKED) {
@@ -239,7 +248,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 					cj[u] = scol[(j0 + u) * kSliceRows];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? safe : cj[u]));
+					xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? 0u : cj[u]));
 				__syncwarp();
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++) {
@@ -256,7 +265,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			for (; j0 < width; j0++) {
 				const uint32_t cj = scol[j0 * kSliceRows];
 				const double v = sval[j0 * kSliceRows];
-				const double xj = ld_gather_f64(x + (cj == kPadCol ? safe : cj));
+				const double xj = ld_gather_f64(x + (cj == kPadCol ? 0u : cj));
 				const double t = __dmul_rn(v, xj);
 				acc = (cj == kPadCol) ? acc : __dadd_rn(acc, t);
 				if (cj == row) {
@@ -269,7 +278,6 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			// one node id per 2x2 block; lanes 2k, 2k+1 (the two dofs of a node) share it
 			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + (lane >> 1);
 			const uint32_t nblk = width >> 1;
-			const uint32_t safe_node = safe >> 1;
 			const uint32_t my_node = row >> 1;
 			uint32_t b0 = 0;
 			for (; b0 + kGatherBatch <= nblk; b0 += kGatherBatch) {
@@ -280,7 +288,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 					cb[u] = scol[(b0 + u) * 16u];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? safe_node : cb[u]));
+					xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
 				__syncwarp();
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++) {
@@ -301,7 +309,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			for (; b0 < nblk; b0++) {
 				const uint32_t cb = scol[b0 * 16u];
 				const double v0 = sval[(2 * b0) * kSliceRows], v1 = sval[(2 * b0 + 1) * kSliceRows];
-				const double2 xb = ld_gather_f64x2(x + 2 * (size_t)(cb == kPadCol ? safe_node : cb));
+				const double2 xb = ld_gather_f64x2(x + 2 * (size_t)(cb == kPadCol ? 0u : cb));
 				const bool pad = cb == kPadCol;
 				const double t0 = __dmul_rn(v0, xb.x);
 				acc = pad ? acc : __dadd_rn(acc, t0);

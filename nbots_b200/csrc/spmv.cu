@@ -11,17 +11,17 @@ constexpr int kSpmvUnroll = 6;
 
 __global__ void __launch_bounds__(kBlock, 4)
 spmv_sell_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
-		 const double *__restrict__ val, const uint32_t *__restrict__ col,
+		 const uint32_t *__restrict__ perm, const double *__restrict__ val, const uint32_t *__restrict__ col,
 		 const double *__restrict__ x, double *__restrict__ y)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
-		const uint32_t row = s * kSliceRows + lane;
+		const uint32_t row = perm ? __ldg(perm + (size_t)s * kSliceRows + lane) : s * kSliceRows + lane;
 		const uint32_t off = __ldg(slice_off + s);
 		const uint32_t width = __ldg(slice_off + s + 1) - off;
 		const double acc = sell_row_times<kSpmvUnroll, false>(val, col, off, width, lane, row,
-								      min(row, N - 1), x, nullptr);
+								      0u, x, nullptr);
 		if (row < N)
 			y[row] = acc;
 	}
@@ -121,7 +121,8 @@ int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out)
 		SellView V;
 		V.N = A->N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
 		V.col = A->blocked ? A->d_bcol : A->d_col;
-	V.uniform_width = A->uniform_width;
+		V.uniform_width = A->uniform_width;
+		V.perm = A->d_perm;
 		if (A->blocked)
 			spmv_stream_kernel<true><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
 		else
@@ -130,7 +131,7 @@ int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out)
 		return NBGPU_OK;
 	}
 	spmv_sell_kernel<<<spmv_grid(A->n_slices), kBlock, 0, ctx().stream>>>(
-		A->N, A->n_slices, A->d_slice_off, A->d_val, A->d_col, d_in, d_out);
+		A->N, A->n_slices, A->d_slice_off, A->d_perm, A->d_val, A->d_col, d_in, d_out);
 	NB_LAUNCHED();
 	return NBGPU_OK;
 }

@@ -50,8 +50,13 @@ class Mesh2D:
         return self.sgm_nodes[off:off + int(self.sgm_sizes[s])]
 
 
-def structured_mesh(nx: int, ny: int, lx: float, ly: float, kind: int = 1) -> Mesh2D:
+def structured_mesh(nx: int, ny: int, lx: float, ly: float, kind: int = 1,
+                    diagonal_seed: int | None = None) -> Mesh2D:
     """(nx x ny)-cell grid on [0,lx]x[0,ly]; quads, or each cell split in 2 triangles.
+
+    With diagonal_seed the splitting diagonal of every cell is drawn at random, which
+    gives the nodes 4 to 8 neighbours -- the ragged row lengths of an unstructured
+    (Delaunay) triangle mesh, at any size, without a mesher.
 
     Input segments (CCW loop): 0 bottom y=0 (left to right), 1 right x=lx (bottom
     to top), 2 top (right to left), 3 left x=0 (top to bottom).  Input vertices:
@@ -76,10 +81,15 @@ def structured_mesh(nx: int, ny: int, lx: float, ly: float, kind: int = 1) -> Me
     else:
         t0 = np.stack([n00, n10, n11], axis=1)
         t1 = np.stack([n00, n11, n01], axis=1)
+        d_edges = np.stack([n00, n11], axis=1)
+        if diagonal_seed is not None:
+            flip = np.random.default_rng(diagonal_seed).integers(0, 2, n00.size).astype(bool)
+            t0[flip] = np.stack([n00, n10, n01], axis=1)[flip]
+            t1[flip] = np.stack([n10, n11, n01], axis=1)[flip]
+            d_edges[flip] = np.stack([n10, n01], axis=1)[flip]
         adj = np.empty((2 * n00.size, 3), dtype=np.uint32)
         adj[0::2] = t0
         adj[1::2] = t1
-        d_edges = np.stack([n00, n11], axis=1)
         edges = np.concatenate([h_edges, v_edges, d_edges])
 
     bottom = nid[0, :]

@@ -9,9 +9,11 @@ import ctypes as C
 
 L = capi.lib(); capi.check(L.nbgpu_init(0))
 which = sys.argv[1] if len(sys.argv) > 1 else "q1"
-if which.startswith("q"):
-    nx, ny = {"q1": (1000, 500), "q4": (2000, 1000), "q16": (4000, 2000)}[which]
-    m = meshgen.structured_mesh(nx, ny, 2.0, 1.0)
+if which[0] in "qt":
+    nx, ny = {"1": (1000, 500), "4": (2000, 1000), "16": (4000, 2000)}[which[1:]]
+    # t<n>: triangles with random diagonals -- ragged rows like an unstructured mesh
+    m = meshgen.structured_mesh(nx, ny, 2.0, 1.0) if which[0] == "q" else \
+        meshgen.structured_mesh(nx, ny, 2.0, 1.0, kind=0, diagonal_seed=1)
     rs, cols = api.pattern_from_mesh(m)
     K = api.Matrix.from_csr(rs, cols)
     mesh = api.Mesh(m)
@@ -51,6 +53,6 @@ api.timer_start()
 st, it, res = K.pcg_jacobi(d_b, d_x, max_iter=400, tol=0.0)
 ms_pcg = api.timer_stop()
 env = {k: v for k, v in os.environ.items() if k.startswith("NBGPU_")}
-print(f"{which} N={N} nnz={nnz} env={env} | spmv {ms*1e3:.1f} us = {bytes_spmv/ms/1e6:.0f} GB/s ({bytes_spmv/ms/1e6/6551.7*100:.1f}%) | "
+print(f"{which} N={N} nnz={nnz} sigma={K.sigma} stored/nnz={K.stored/nnz:.3f} env={env} | spmv {ms*1e3:.1f} us = {bytes_spmv/ms/1e6:.0f} GB/s ({bytes_spmv/ms/1e6/6551.7*100:.1f}%) | "
       f"K1 {per[0]*1e3:.1f} us ({bytes_spmv/per[0]/1e6:.0f} GB/s) K2 {per[1]*1e3:.1f} K3 {per[2]*1e3:.1f} | "
       f"pcg {ms_pcg/it*1e3:.1f} us/iter = {N*it/ms_pcg/1e6:.2f} GDOFit/s")
