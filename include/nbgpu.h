@@ -256,6 +256,19 @@ int nbgpu_stress_from_strain(uint32_t N_elems, uint32_t N_gp,
 			     const uint8_t *enabled, const double *d_strain,
 			     double *d_stress);
 
+/* nb_fem_interpolate_from_gpoints_to_nodes (finite_element/gaussp_to_nodes.c:50-75):
+ * lumped-mass projection of N_comp values per Gauss point onto the nodes,
+ * d_gp_values[(elem * N_gp + gp) * N_comp + c] -> d_nodal_values[node * N_comp + c].
+ * Returns 1 when an element is distorted (detJ < 0); the reference leaves the
+ * output untouched in that case, here its contents are then unspecified. */
+int nbgpu_gp_to_nodes(const nbgpu_mesh_t *mesh,
+		      const nbgpu_elem_tables_t *tables, uint32_t N_comp,
+		      const double *d_gp_values, double *d_nodal_values);
+/* nb_pde_get_vm_stress / nb_pde_get_main_stress (common_solid_mechanics/formulas.c:65-77)
+ * over n_points stress triplets [sxx, syy, sxy]; d_main gets 2 values per point */
+int nbgpu_von_mises(uint64_t n_points, const double *d_stress, double *d_vm);
+int nbgpu_main_stress(uint64_t n_points, const double *d_stress, double *d_main);
+
 /* ------------------------------------------- boundary-condition lists -- */
 
 /* value callback of a function-valued condition, as nb_bcond_push_function

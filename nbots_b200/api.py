@@ -248,6 +248,11 @@ class Mesh:
     def compute_strain(self, d_disp: DeviceBuffer, d_strain: DeviceBuffer):
         check(lib().nbgpu_compute_strain(self.h, C.byref(self.tables), d_disp.ptr, d_strain.ptr))
 
+    def gp_to_nodes(self, n_comp: int, d_gp_values: DeviceBuffer, d_nodal: DeviceBuffer) -> int:
+        """nb_fem_interpolate_from_gpoints_to_nodes; returns 0, or 1 for a distorted element."""
+        return check(lib().nbgpu_gp_to_nodes(self.h, C.byref(self.tables), n_comp, d_gp_values.ptr, d_nodal.ptr),
+                     ok=(capi.OK, capi.DISTORTED_ELEMENT))
+
     def destroy(self):
         if self.h:
             lib().nbgpu_mesh_destroy(self.h)
@@ -271,6 +276,14 @@ def stress_from_strain(n_elems, n_gp, D, d_strain: DeviceBuffer, d_stress: Devic
     en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
     check(lib().nbgpu_stress_from_strain(n_elems, n_gp, _ptr(D, f64p), _ptr(Dv, f64p), _ptr(en, u8p), d_strain.ptr,
                                          d_stress.ptr))
+
+
+def von_mises(n_points, d_stress: DeviceBuffer, d_vm: DeviceBuffer):
+    check(lib().nbgpu_von_mises(n_points, d_stress.ptr, d_vm.ptr))
+
+
+def main_stress(n_points, d_stress: DeviceBuffer, d_main: DeviceBuffer):
+    check(lib().nbgpu_main_stress(n_points, d_stress.ptr, d_main.ptr))
 
 
 def timer_start():

@@ -101,6 +101,9 @@ SIGNATURES = {
     "nbgpu_vector_add_entries_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "nbgpu_compute_strain": (C.c_int, [C.c_void_p, C.POINTER(ElemTables), C.c_void_p, C.c_void_p]),
     "nbgpu_stress_from_strain": (C.c_int, [C.c_uint32, C.c_uint32, f64p, f64p, u8p, C.c_void_p, C.c_void_p]),
+    "nbgpu_gp_to_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "nbgpu_von_mises": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p]),
+    "nbgpu_main_stress": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p]),
     "nbgpu_fem_session_create": (C.c_int, [C.c_void_p, C.c_void_p, f64p, C.c_double, C.c_uint32, u32p, f64p, C.c_uint32,
                                            u32p, f64p, C.c_int, f64p, C.c_double, C.c_int, vpp]),
     "nbgpu_fem_session_step": (C.c_int, [C.c_void_p, u8p, f64p, C.c_int, C.c_uint32, C.c_double, C.c_void_p]),

@@ -452,6 +452,88 @@ stress_kernel(uint32_t N_elems, uint32_t NGP, const uint8_t *__restrict__ enable
 	t[2] = s2 * d3;
 }
 
+// ---- Gauss points -> nodes (gaussp_to_nodes.c:50-218) ------------------------------
+// Lumped-mass L2 projection.  One thread per (node, component): it walks the elements around its
+// node in ascending element id -- the order in which the reference's serial element loop adds into
+// M[v] and b[v][c] (:186-196) -- so the quotient b / M comes out bit-identical.
+template <int NPE, int NGP>
+__global__ void __launch_bounds__(kBlock)
+gp_to_nodes_kernel(uint32_t N_nod, uint32_t N_comp, const double *__restrict__ nod,
+		   const uint32_t *__restrict__ adj, const uint32_t *__restrict__ n2e_ptr,
+		   const uint32_t *__restrict__ n2e, const double *__restrict__ gp_values,
+		   double *__restrict__ nodal, unsigned int *first_bad)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (size_t)N_nod * N_comp)
+		return;
+	const uint32_t node = (uint32_t)(t / N_comp), c = (uint32_t)(t % N_comp);
+	double M = 0.0, b = 0.0;
+	for (uint32_t k = n2e_ptr[node]; k < n2e_ptr[node + 1]; k++) {
+		const uint32_t e = n2e[k];
+		uint32_t v[NPE];
+		double xs[NPE], ys[NPE];
+#pragma unroll
+		for (int i = 0; i < NPE; i++) {
+			v[i] = adj[(size_t)e * NPE + i];
+			xs[i] = nod[2 * (size_t)v[i]];
+			ys[i] = nod[2 * (size_t)v[i] + 1];
+		}
+		// a node listed twice by an element receives both local rows, as in the reference
+#pragma unroll
+		for (int i = 0; i < NPE; i++) {
+			if (v[i] != node)
+				continue;
+			double Me = 0.0, be = 0.0;
+			bool bad = false;
+#pragma unroll
+			for (int gp = 0; gp < NGP; gp++) {
+				double dx[NPE], dy[NPE];
+				const double detJ = jacobian_gradients<NPE, NGP>(xs, ys, gp, dx, dy);
+				if (detJ < 0)
+					bad = true;
+				const double wp = c_tab.w[gp];
+				const double Ni = c_tab.Ni[i * NGP + gp];
+#pragma unroll
+				for (int j = 0; j < NPE; j++)
+					Me += Ni * c_tab.Ni[j * NGP + gp] * detJ * wp;      // :163-167
+				const double integral = Ni * detJ * wp;                     // :171
+				be += gp_values[((size_t)e * NGP + gp) * N_comp + c] * integral;
+			}
+			if (bad) {
+				atomicMin(first_bad, e);
+				continue;
+			}
+			M += Me;
+			b += be;
+		}
+	}
+	nodal[t] = b / M;
+}
+
+__global__ void __launch_bounds__(kBlock)
+von_mises_kernel(size_t n, const double *__restrict__ stress, double *__restrict__ vm)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const double sxx = stress[3 * i], syy = stress[3 * i + 1], sxy = stress[3 * i + 2];
+	vm[i] = sqrt(sxx * sxx + syy * syy - sxx * syy + 3.0 * (sxy * sxy));   // formulas.c:65-68
+}
+
+__global__ void __launch_bounds__(kBlock)
+main_stress_kernel(size_t n, const double *__restrict__ stress, double *__restrict__ out)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const double sxx = stress[3 * i], syy = stress[3 * i + 1], sxy = stress[3 * i + 2];
+	// formulas.c:70-77 exactly as the reference writes it (radius from the MEAN stress)
+	const double avg = (sxx + syy) / 2.0;
+	const double R = sqrt(avg * avg + sxy * sxy);
+	out[2 * i] = avg + R;
+	out[2 * i + 1] = avg - R;
+}
+
 // ---- host helpers ------------------------------------------------------------
 
 int upload_tables(const nbgpu_elem_tables_t *t, uint32_t npe)
@@ -908,6 +990,63 @@ int nbgpu_compute_strain(const nbgpu_mesh_t *m, const nbgpu_elem_tables_t *table
 	else
 		strain_kernel<4, 4><<<grid, kBlock, 0, ctx().stream>>>(m->N_elems, m->d_nod, m->d_adj, d_disp,
 								       d_strain);
+	NB_LAUNCHED();
+	return NBGPU_OK;
+}
+
+int nbgpu_gp_to_nodes(const nbgpu_mesh_t *m, const nbgpu_elem_tables_t *tables, uint32_t N_comp,
+		      const double *d_gp_values, double *d_nodal_values)
+{
+	NB_INIT();
+	NB_ARG(m != nullptr && d_gp_values != nullptr && d_nodal_values != nullptr && N_comp > 0);
+	NB_TRY(upload_tables(tables, m->npe));
+	if (m->N_nod == 0)
+		return NBGPU_OK;
+	Context &c = ctx();
+	unsigned int *d_bad = nullptr;
+	NB_CUDA(cudaMalloc(&d_bad, sizeof(unsigned int)));
+	cudaMemsetAsync(d_bad, 0xFF, sizeof(unsigned int), c.stream);
+	const size_t n = (size_t)m->N_nod * N_comp;
+	const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+	if (m->npe == 3)
+		gp_to_nodes_kernel<3, 1><<<grid, kBlock, 0, c.stream>>>(m->N_nod, N_comp, m->d_nod, m->d_adj, m->d_n2e_ptr,
+								       m->d_n2e, d_gp_values, d_nodal_values, d_bad);
+	else
+		gp_to_nodes_kernel<4, 4><<<grid, kBlock, 0, c.stream>>>(m->N_nod, N_comp, m->d_nod, m->d_adj, m->d_n2e_ptr,
+								       m->d_n2e, d_gp_values, d_nodal_values, d_bad);
+	c.launches++;
+	unsigned int bad = 0xFFFFFFFFu;
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c.stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(c.stream);
+	cudaFree(d_bad);
+	if (e != cudaSuccess) {
+		set_error("gp_to_nodes: %s", cudaGetErrorString(e));
+		return NBGPU_ERR_CUDA;
+	}
+	return bad == 0xFFFFFFFFu ? NBGPU_OK : NBGPU_DISTORTED_ELEMENT;
+}
+
+int nbgpu_von_mises(uint64_t n_points, const double *d_stress, double *d_vm)
+{
+	NB_INIT();
+	NB_ARG(d_stress != nullptr && d_vm != nullptr);
+	if (n_points == 0)
+		return NBGPU_OK;
+	von_mises_kernel<<<(unsigned)((n_points + kBlock - 1) / kBlock), kBlock, 0, ctx().stream>>>(n_points, d_stress, d_vm);
+	NB_LAUNCHED();
+	return NBGPU_OK;
+}
+
+int nbgpu_main_stress(uint64_t n_points, const double *d_stress, double *d_main)
+{
+	NB_INIT();
+	NB_ARG(d_stress != nullptr && d_main != nullptr);
+	if (n_points == 0)
+		return NBGPU_OK;
+	main_stress_kernel<<<(unsigned)((n_points + kBlock - 1) / kBlock), kBlock, 0, ctx().stream>>>(n_points, d_stress, d_main);
 	NB_LAUNCHED();
 	return NBGPU_OK;
 }

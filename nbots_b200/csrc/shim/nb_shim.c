@@ -345,6 +345,46 @@ int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh
 	return st != NBGPU_OK ? st : status;
 }
 
+/* headers/nb/pde_bot/finite_element/gaussp_to_nodes.h:9-14.  The output is written only on success,
+ * like the reference (gaussp_to_nodes.c:66-72). */
+int nb_fem_interpolate_from_gpoints_to_nodes(const nb_mesh2D_t *const part, const nb_fem_elem_t *const elem,
+					     uint32_t N_comp, const double *gp_values, double *nodal_values)
+{
+	resolve();
+	nbgpu_elem_tables_t tab;
+	read_tables(elem, &tab);
+	flat_mesh_t fm;
+	nbgpu_mesh_t *dmesh = NULL;
+	double *d_gp = NULL, *d_nod = NULL;
+	int status = 1;
+	int st = flatten_mesh(part, tab.N_nodes, 0, &fm);
+	const size_t gp_bytes = (size_t)fm.d.N_elems * tab.N_gp * N_comp * sizeof(double);
+	const size_t nod_bytes = (size_t)fm.d.N_nod * N_comp * sizeof(double);
+	if (st == NBGPU_OK)
+		st = nbgpu_mesh_create(fm.d.N_nod, fm.d.nod, fm.d.N_elems, fm.d.nodes_per_elem, fm.d.adj, &dmesh);
+	if (st == NBGPU_OK)
+		st = nbgpu_malloc((void **)&d_gp, gp_bytes + 8);
+	if (st == NBGPU_OK)
+		st = nbgpu_malloc((void **)&d_nod, nod_bytes + 8);
+	if (st == NBGPU_OK && gp_bytes)
+		st = nbgpu_copy_h2d(d_gp, gp_values, gp_bytes);
+	if (st == NBGPU_OK) {
+		st = nbgpu_gp_to_nodes(dmesh, &tab, N_comp, d_gp, d_nod);
+		if (st == NBGPU_OK || st == NBGPU_DISTORTED_ELEMENT) {
+			status = st;
+			st = NBGPU_OK;
+			if (status == NBGPU_OK && nod_bytes)
+				st = nbgpu_copy_d2h(nodal_values, d_nod, nod_bytes);
+		}
+	}
+	nbgpu_free(d_gp);
+	nbgpu_free(d_nod);
+	nbgpu_mesh_destroy(dmesh);
+	free_mesh(&fm);
+	report("nb_fem_interpolate_from_gpoints_to_nodes", st);
+	return st != NBGPU_OK ? st : status;
+}
+
 /* growable ordered dof list */
 typedef struct {
 	uint32_t n, cap;

@@ -109,8 +109,13 @@ def fem_case(name, m, rm, bcs, E, nu, analysis=0, thickness=1.0, density=0.0, se
         assert np.array_equal(disp, x), "driver and step-by-step solve disagree"
     strain_x = ref.compute_strain(rm, kind, x, m.n_elems, ngp)
     stress = ref.stress_from_strain(m.n_elems, kind, E, nu, analysis, strain_x, enabled)
+    # post-processing next to the solve: nodal projection (gaussp_to_nodes.c), von Mises, main stresses
+    st_nod, stress_nod = ref.gp_to_nodes(rm, kind, m.n_nod, 3, stress)
+    assert st_nod == 0
+    vm = ref.vm_stress(stress)
+    main = ref.main_stress(stress)
     y = K.spmv(x)
-    data = dict(kind=kind, nod=m.nod, edg=m.edg, adj=m.adj, vtx=m.vtx, sgm_sizes=m.sgm_sizes, sgm_nodes=m.sgm_nodes,
+    data = dict(stress_nod=stress_nod, vm=vm, main_stress=main, kind=kind, nod=m.nod, edg=m.edg, adj=m.adj, vtx=m.vtx, sgm_sizes=m.sgm_sizes, sgm_nodes=m.sgm_nodes,
                 E=E, nu=nu, analysis=analysis, thickness=thickness, density=density, self_weight=int(self_weight),
                 gravity=np.array(gravity), tol=tol, rows_size=rows_size, cols=cols, K_pre=K_pre, F_pre=F_pre,
                 K_post=K_post, F_post=F_post, x=x, pcg_status=st, pcg_iters=iters, pcg_res=res, x_cg=x_cg,

@@ -65,6 +65,11 @@ def lib():
         L.nbo_compute_strain.argtypes = [f64p, C.c_uint32, C.c_int, u32p, f64p, f64p]
         L.nbo_stress_from_strain.argtypes = [C.c_uint32, C.c_int, C.c_double, C.c_double, C.c_int, f64p, u8p, f64p]
         L.nbo_kirsch_stress.argtypes = [C.c_double, C.c_double, f64p]
+        L.nbo_gp_to_nodes.restype = C.c_int
+        L.nbo_gp_to_nodes.argtypes = [C.c_uint32, f64p, C.c_uint32, C.c_int, u32p, C.c_uint32, f64p, f64p]
+        L.nbo_vm_stress.restype = C.c_double
+        L.nbo_vm_stress.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.nbo_main_stress.argtypes = [C.c_double, C.c_double, C.c_double, f64p]
         _lib = L
     return _lib
 
@@ -205,6 +210,29 @@ def compute_strain(m, disp):
     st = lib().nbo_compute_strain(_p(m.nod, f64p), m.n_elems, m.kind, _p(m.adj, u32p), _p(disp, f64p),
                                   _p(strain, f64p))
     return st, strain
+
+
+def gp_to_nodes(m, n_comp, gp_values):
+    gp_values = np.ascontiguousarray(gp_values, dtype=np.float64)
+    out = np.zeros(m.n_nod * n_comp)
+    st = lib().nbo_gp_to_nodes(m.n_nod, _p(m.nod, f64p), m.n_elems, m.kind, _p(m.adj, u32p), n_comp,
+                               _p(gp_values, f64p), _p(out, f64p))
+    return st, out
+
+
+def vm_stress(stress):
+    s = np.asarray(stress, dtype=np.float64).reshape(-1, 3)
+    return np.array([lib().nbo_vm_stress(a, b, c) for a, b, c in s])
+
+
+def main_stress(stress):
+    s = np.asarray(stress, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((s.shape[0], 2))
+    tmp = np.zeros(2)
+    for i, (a, b, c) in enumerate(s):
+        lib().nbo_main_stress(a, b, c, _p(tmp, f64p))
+        out[i] = tmp
+    return out.ravel()
 
 
 def stress_from_strain(n_elems, elem_type, E, nu, analysis, strain, enabled=None):

@@ -121,6 +121,15 @@ void nbo_stress_from_strain(uint32_t N_elems, int elem_type, double E,
 
 void nbo_kirsch_stress(double x, double y, double s[3]);
 
+/* gaussp_to_nodes.c:50-218 */
+int nbo_gp_to_nodes(uint32_t N_nod, const double *nod, uint32_t N_elems,
+		    int elem_type, const uint32_t *adj, uint32_t N_comp,
+		    const double *gp_values, double *nodal_values);
+
+/* formulas.c:65-77 */
+double nbo_vm_stress(double sxx, double syy, double sxy);
+void nbo_main_stress(double sxx, double syy, double sxy, double main_stress[2]);
+
 #ifdef __cplusplus
 }
 #endif

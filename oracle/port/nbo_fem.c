@@ -417,3 +417,81 @@ void nbo_stress_from_strain(uint32_t N_elems, int elem_type, double E,
 		}
 	}
 }
+
+/* Reference: finite_element/gaussp_to_nodes.c:50-218
+ * (nb_fem_interpolate_from_gpoints_to_nodes).  Lumped-mass L2 projection of
+ * Gauss-point values onto the nodes: M[v] = sum_e sum_gp sum_j Ni Nj detJ w,
+ * b[v][c] = sum_e sum_gp val(e,gp,c) Ni detJ w, nodal = b / M.  Returns 1 at
+ * the first element with detJ < 0 (nodal_values then stay untouched, :69-70). */
+int nbo_gp_to_nodes(uint32_t N_nod, const double *nod, uint32_t N_elems,
+		    int elem_type, const uint32_t *adj, uint32_t N_comp,
+		    const double *gp_values, double *nodal_values)
+{
+	elem_t el;
+	nbo_elem_tables(elem_type, &el.n, &el.ngp, el.w, el.Ni, el.dpsi,
+			el.deta);
+	double *M = calloc(N_nod ? N_nod : 1, sizeof(double));
+	double *b = calloc((size_t)N_nod * N_comp + 1, sizeof(double));
+	double *be = malloc(((size_t)4 * N_comp + 1) * sizeof(double));
+	int status = 0;
+	for (uint32_t e = 0; e < N_elems && !status; e++) {
+		const uint32_t *v = adj + (size_t)el.n * e;
+		double Me[4] = {0, 0, 0, 0};
+		memset(be, 0, (size_t)4 * N_comp * sizeof(double));
+		for (uint32_t gp = 0; gp < el.ngp; gp++) {
+			double dx[4], dy[4];
+			double detJ = jacobian_and_gradients(&el, nod, v, gp,
+							     dx, dy);
+			if (detJ < 0) {
+				status = 1;
+				break;
+			}
+			double wp = el.w[gp];
+			for (uint32_t i = 0; i < el.n; i++) {          /* :160-176 */
+				double Ni = el.Ni[i * el.ngp + gp];
+				for (uint32_t j = 0; j < el.n; j++) {
+					double Nj = el.Ni[j * el.ngp + gp];
+					double integral = Ni * Nj * detJ * wp;
+					Me[i] += integral;
+				}
+				size_t ggp = (size_t)e * el.ngp + gp;
+				double integral = Ni * detJ * wp;
+				for (uint32_t c = 0; c < N_comp; c++)
+					be[i * N_comp + c] +=
+						gp_values[ggp * N_comp + c] * integral;
+			}
+		}
+		if (status)
+			break;
+		for (uint32_t i = 0; i < el.n; i++) {                  /* :186-196 */
+			M[v[i]] += Me[i];
+			for (uint32_t c = 0; c < N_comp; c++)
+				b[(size_t)v[i] * N_comp + c] += be[i * N_comp + c];
+		}
+	}
+	if (!status)
+		for (size_t i = 0; i < (size_t)N_nod; i++)             /* :199-209 */
+			for (uint32_t c = 0; c < N_comp; c++)
+				nodal_values[i * N_comp + c] =
+					b[i * N_comp + c] / M[i];
+	free(M);
+	free(b);
+	free(be);
+	return status;
+}
+
+/* Reference: common_solid_mechanics/formulas.c:65-68 */
+double nbo_vm_stress(double sxx, double syy, double sxy)
+{
+	return sqrt(sxx * sxx + syy * syy - sxx * syy + 3.0 * (sxy * sxy));
+}
+
+/* Reference: formulas.c:70-77 -- as written there (the radius uses the MEAN
+ * stress, not half the difference; restated, not corrected). */
+void nbo_main_stress(double sxx, double syy, double sxy, double main_stress[2])
+{
+	double avg = (sxx + syy) / 2.0;
+	double R = sqrt(avg * avg + sxy * sxy);
+	main_stress[0] = avg + R;
+	main_stress[1] = avg - R;
+}

@@ -77,6 +77,15 @@ def lib():
         L.refh_fem_static.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                       C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p, f64p, f64p]
         L.refh_compute_strain.argtypes = [C.c_void_p, C.c_int, f64p, f64p]
+        L.refh_sparse_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.refh_sparse_save_mat4.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.refh_mat4_save_vec.argtypes = [C.c_char_p, C.c_char_p, f64p, C.c_uint32]
+        L.refh_mesh_save_vtk.restype = C.c_int
+        L.refh_mesh_save_vtk.argtypes = [C.c_void_p, C.c_char_p]
+        L.refh_gp_to_nodes.restype = C.c_int
+        L.refh_gp_to_nodes.argtypes = [C.c_void_p, C.c_int, C.c_uint32, f64p, f64p]
+        L.refh_vm_stress.argtypes = [C.c_uint32, f64p, f64p]
+        L.refh_main_stress.argtypes = [C.c_uint32, f64p, f64p]
         L.refh_stress_from_strain.argtypes = [C.c_uint32, C.c_int, C.c_double, C.c_double, C.c_int, f64p,
                                               u8p, f64p]
         _lib = L
@@ -278,6 +287,27 @@ def compute_strain(mesh: RefMesh, elem_type, disp, n_elems, n_gp):
     strain = np.zeros(3 * n_gp * n_elems)
     lib().refh_compute_strain(mesh.h, elem_type, _p(disp, f64p), _p(strain, f64p))
     return strain
+
+
+def gp_to_nodes(mesh: RefMesh, elem_type, n_nod, n_comp, gp_values):
+    gp_values = np.ascontiguousarray(gp_values, dtype=np.float64)
+    out = np.zeros(n_nod * n_comp)
+    st = lib().refh_gp_to_nodes(mesh.h, elem_type, n_comp, _p(gp_values, f64p), _p(out, f64p))
+    return st, out
+
+
+def vm_stress(stress):
+    stress = np.ascontiguousarray(stress, dtype=np.float64)
+    vm = np.zeros(stress.size // 3)
+    lib().refh_vm_stress(vm.size, _p(stress, f64p), _p(vm, f64p))
+    return vm
+
+
+def main_stress(stress):
+    stress = np.ascontiguousarray(stress, dtype=np.float64)
+    out = np.zeros(2 * (stress.size // 3))
+    lib().refh_main_stress(stress.size // 3, _p(stress, f64p), _p(out, f64p))
+    return out
 
 
 def stress_from_strain(n_elems, elem_type, E, nu, analysis, strain, enabled=None):

@@ -552,4 +552,56 @@ void refh_stress_from_strain(uint32_t N_elems, int elem_type, double E,
 }
 
 /* the reference mesh pointer itself, for the drop-in shim tests */
+/* gaussp_to_nodes.c:50 and formulas.c:65-77, called as they are */
+int refh_gp_to_nodes(const void *hp, int elem_type, uint32_t N_comp,
+		     const double *gp_values, double *nodal_values)
+{
+	const refh_mesh_t *h = hp;
+	nb_fem_elem_t *e = nb_fem_elem_create(elem_type ? NB_QUAD_LINEAR
+							: NB_TRG_LINEAR);
+	int st = nb_fem_interpolate_from_gpoints_to_nodes(h->mesh, e, N_comp,
+							  gp_values,
+							  nodal_values);
+	nb_fem_elem_destroy(e);
+	return st;
+}
+
+void refh_vm_stress(uint32_t n, const double *stress, double *vm)
+{
+	for (uint32_t i = 0; i < n; i++)
+		vm[i] = nb_pde_get_vm_stress(stress[3 * i], stress[3 * i + 1],
+					     stress[3 * i + 2]);
+}
+
+void refh_main_stress(uint32_t n, const double *stress, double *main_stress)
+{
+	for (uint32_t i = 0; i < n; i++)
+		nb_pde_get_main_stress(stress[3 * i], stress[3 * i + 1],
+				       stress[3 * i + 2], main_stress + 2 * i);
+}
+
+/* on-disk formats written by the reference itself (sparse.c:97-112,
+ * matlab_v4.c:184-250 and :537-564, mesh2D_file_format_vtk.c:23-89) */
+void refh_sparse_save(const void *A, const char *path) { nb_sparse_save(A, path); }
+
+void refh_sparse_save_mat4(const void *A, const char *path, const char *label)
+{
+	char buf[64];
+	snprintf(buf, sizeof(buf), "%s", label);
+	nb_sparse_save_mat4(A, path, buf);
+}
+
+void refh_mat4_save_vec(const char *path, const char *label, const double *x,
+			uint32_t N)
+{
+	char buf[64];
+	snprintf(buf, sizeof(buf), "%s", label);
+	nb_mat4_save_vec(path, buf, x, N);
+}
+
+int refh_mesh_save_vtk(const void *hp, const char *path)
+{
+	return nb_mesh2D_save_vtk(((const refh_mesh_t *)hp)->mesh, path);
+}
+
 void *refh_mesh_ptr(const void *hp) { return ((const refh_mesh_t *)hp)->mesh; }

@@ -29,7 +29,7 @@ SCRIPT = textwrap.dedent('''
     L = ref.lib()
     # the reference's PLT entries now point at the shim
     for name in ("nb_sparse_solve_CG_precond_Jacobi", "nb_fem_compute_2D_Solid_Mechanics",
-                 "pipeline_assemble_system"):
+                 "pipeline_assemble_system", "nb_fem_interpolate_from_gpoints_to_nodes"):
         assert C.cast(getattr(shim, name), C.c_void_p).value != C.cast(getattr(L, name), C.c_void_p).value
     before = capi.lib().nbgpu_launch_count()
     for name in ("beam_cantilever_trg1000", "quad_void_selfweight_24x8", "plate_with_hole_trg1000"):
@@ -61,6 +61,9 @@ SCRIPT = textwrap.dedent('''
         assert st == 0
         if float(g["tol"]) == 1e-8:     # the driver's fixed tolerance (static_elasticity2D.c:88)
             assert rel_l2(disp, g["x"]) <= 1e-10 and rel_l2(strain, g["strain"]) <= 1e-9, name
+        # (4) post-processing entry: Gauss points -> nodes through the shim, on the reference's mesh object
+        st, nodal = ref.gp_to_nodes(rm, kind, m.n_nod, 3, g["stress"])
+        assert st == 0 and np.array_equal(nodal, g["stress_nod"]), name
         if name.startswith("beam"):
             assert abs(np.sqrt((disp.reshape(-1, 2) ** 2).sum(axis=1)).max() - 1.00701e-1) < 1e-6
     launched = capi.lib().nbgpu_launch_count() - before

@@ -303,6 +303,39 @@ def test_strain_and_stress_bit_exact(nbgpu_lib, name):
     en = g["enabled"] if "enabled" in g.files else None
     api.stress_from_strain(m.n_elems, ngp, g["D"], d_e, d_s, enabled=en)
     assert np.array_equal(d_s.to_host(), g["stress"])
+    # the post-processing that follows in the reference's callers: nodal projection, von Mises, main stresses
+    d_n = api.DeviceBuffer.zeros(3 * m.n_nod)
+    assert mesh.gp_to_nodes(3, d_s, d_n) == 0
+    assert np.array_equal(d_n.to_host(), g["stress_nod"])              # gaussp_to_nodes.c:50
+    n_pts = ngp * m.n_elems
+    d_vm = api.DeviceBuffer.zeros(n_pts)
+    d_ms = api.DeviceBuffer.zeros(2 * n_pts)
+    api.von_mises(n_pts, d_s, d_vm)
+    api.main_stress(n_pts, d_s, d_ms)
+    assert np.array_equal(d_vm.to_host(), g["vm"])                     # formulas.c:65-68
+    assert np.array_equal(d_ms.to_host(), g["main_stress"])            # formulas.c:70-77
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_gp_to_nodes_components_and_distortion(nbgpu_lib, kind):
+    rng = np.random.default_rng(21 + kind)
+    m = meshgen.structured_mesh(37, 23, 2.0, 1.0, kind=kind, diagonal_seed=5 if kind == 0 else None)
+    m.nod += (rng.random(m.nod.size) - 0.5) * 0.01
+    mesh = api.Mesh(m)
+    ngp = 4 if kind else 1
+    for n_comp in (1, 2, 5):
+        gp = rng.standard_normal(m.n_elems * ngp * n_comp)
+        d_gp = api.DeviceBuffer.from_host(gp)
+        d_n = api.DeviceBuffer.zeros(m.n_nod * n_comp)
+        assert mesh.gp_to_nodes(n_comp, d_gp, d_n) == 0
+        st, want = port.gp_to_nodes(m, n_comp, gp)
+        assert st == 0 and np.array_equal(d_n.to_host(), want)
+    npe = m.npe
+    m.adj[npe * 7:npe * 8] = m.adj[npe * 7:npe * 8][::-1].copy()        # clockwise element
+    bad = api.Mesh(m)
+    d_gp = api.DeviceBuffer.from_host(rng.standard_normal(m.n_elems * ngp))
+    d_n = api.DeviceBuffer.zeros(m.n_nod)
+    assert bad.gp_to_nodes(1, d_gp, d_n) == 1 == port.gp_to_nodes(m, 1, d_gp.to_host())[0]
 
 
 # ------------------------------------------------------------------------ driver --

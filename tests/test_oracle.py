@@ -35,6 +35,10 @@ def test_port_reproduces_reference_fem_pipeline(name):
     assert np.array_equal(strain, g["strain"])
     stress = port.stress_from_strain(m.n_elems, m.kind, float(g["E"]), float(g["nu"]), int(g["analysis"]), strain, en)
     assert np.array_equal(stress, g["stress"])
+    st, nodal = port.gp_to_nodes(m, 3, stress)                          # gaussp_to_nodes.c:50
+    assert st == 0 and np.array_equal(nodal, g["stress_nod"])
+    assert np.array_equal(port.vm_stress(stress), g["vm"])             # formulas.c:65-77
+    assert np.array_equal(port.main_stress(stress), g["main_stress"])
     assert np.array_equal(port.constitutive(float(g["E"]), float(g["nu"]), int(g["analysis"])), g["D"])
 
 
@@ -135,3 +139,14 @@ def test_port_matches_live_reference(kind):
     st2, _ = port.assemble(PK2, m2, 1.0, 0.3)
     assert st == st2 == 1
     assert np.array_equal(K2.export()[2], PK2.vals)      # both hold the elements before the bad one
+    # Gauss-point -> node projection: random field with 1, 3 and 5 components; distorted mesh -> status 1
+    ngp = 4 if kind else 1
+    for n_comp in (1, 3, 5):
+        gp = rng.standard_normal(m.n_elems * ngp * n_comp)
+        (s1, n1), (s2, n2) = ref.gp_to_nodes(rm, kind, m.n_nod, n_comp, gp), port.gp_to_nodes(m, n_comp, gp)
+        assert s1 == s2 == 0 and np.array_equal(n1, n2)
+    gp = rng.standard_normal(m2.n_elems * ngp * 3)
+    assert ref.gp_to_nodes(rm2, kind, m2.n_nod, 3, gp)[0] == port.gp_to_nodes(m2, 3, gp)[0] == 1
+    t = rng.standard_normal(300) * 1e3
+    assert np.array_equal(ref.vm_stress(t), port.vm_stress(t))
+    assert np.array_equal(ref.main_stress(t), port.main_stress(t))
