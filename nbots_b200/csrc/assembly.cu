@@ -581,7 +581,7 @@ int build_coloring(nbgpu_mesh_t *m)
 	std::vector<uint32_t> next(m->color_ptr.begin(), m->color_ptr.end() - 1), elems(m->N_elems);
 	for (uint32_t e = 0; e < m->N_elems; e++)
 		elems[next[color[e]]++] = e;
-	NB_CUDA(cudaMalloc(&m->d_color_elems, std::max<size_t>(1, m->N_elems) * sizeof(uint32_t)));
+	NB_CUDA(nbgpu::dmalloc(&m->d_color_elems, std::max<size_t>(1, m->N_elems) * sizeof(uint32_t)));
 	NB_CUDA(cudaMemcpy(m->d_color_elems, elems.data(), (size_t)m->N_elems * sizeof(uint32_t),
 			   cudaMemcpyHostToDevice));
 	m->n_colors = n_colors;
@@ -719,17 +719,17 @@ int nbgpu_mesh_create(uint32_t N_nod, const double *nod, uint32_t N_elems, uint3
 			n2e.swap(n2e2);
 		}
 	}
-	cudaError_t e = cudaMalloc(&m->d_nod, std::max<size_t>(1, 2 * (size_t)N_nod) * sizeof(double));
+	cudaError_t e = nbgpu::dmalloc(&m->d_nod, std::max<size_t>(1, 2 * (size_t)N_nod) * sizeof(double));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&m->d_adj, std::max<size_t>(1, (size_t)npe * N_elems) * sizeof(uint32_t));
+		e = nbgpu::dmalloc(&m->d_adj, std::max<size_t>(1, (size_t)npe * N_elems) * sizeof(uint32_t));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&m->d_n2e_ptr, ptr.size() * sizeof(uint32_t));
+		e = nbgpu::dmalloc(&m->d_n2e_ptr, ptr.size() * sizeof(uint32_t));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&m->d_n2e, std::max<size_t>(1, n2e.size()) * sizeof(uint32_t));
+		e = nbgpu::dmalloc(&m->d_n2e, std::max<size_t>(1, n2e.size()) * sizeof(uint32_t));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&m->d_enabled, std::max<size_t>(1, N_elems));
+		e = nbgpu::dmalloc(&m->d_enabled, std::max<size_t>(1, N_elems));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&m->d_scale, std::max<size_t>(1, N_elems) * sizeof(double));
+		e = nbgpu::dmalloc(&m->d_scale, std::max<size_t>(1, N_elems) * sizeof(double));
 	if (e == cudaSuccess)
 		e = cudaMemcpy(m->d_nod, nod, 2 * (size_t)N_nod * sizeof(double), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
@@ -755,13 +755,13 @@ int nbgpu_mesh_destroy(nbgpu_mesh_t *m)
 	if (ctx().ready) {
 		cudaSetDevice(ctx().device);
 		cudaStreamSynchronize(ctx().stream);
-		cudaFree(m->d_nod);
-		cudaFree(m->d_adj);
-		cudaFree(m->d_n2e_ptr);
-		cudaFree(m->d_n2e);
-		cudaFree(m->d_enabled);
-		cudaFree(m->d_scale);
-		cudaFree(m->d_color_elems);
+		nbgpu::dfree(m->d_nod);
+		nbgpu::dfree(m->d_adj);
+		nbgpu::dfree(m->d_n2e_ptr);
+		nbgpu::dfree(m->d_n2e);
+		nbgpu::dfree(m->d_enabled);
+		nbgpu::dfree(m->d_scale);
+		nbgpu::dfree(m->d_color_elems);
 	}
 	delete m;
 	return NBGPU_OK;
@@ -801,7 +801,7 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
 	}
 	// flags: [0] lowest distorted element id, [1] pattern miss
 	unsigned int *d_flags = nullptr;
-	NB_CUDA(cudaMalloc(&d_flags, 2 * sizeof(unsigned int)));
+	NB_CUDA(nbgpu::dmalloc(&d_flags, 2 * sizeof(unsigned int)));
 	const unsigned int init_flags[2] = {0xFFFFFFFFu, 0u};
 	NB_CUDA(cudaMemcpyAsync(d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, c.stream));
 	// nb_sparse_reset (pipeline.c:54) -- F is zeroed/overwritten by the kernels (pipeline.c:57)
@@ -815,7 +815,7 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
 	cudaError_t e = cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c.stream);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(c.stream);
-	cudaFree(d_flags);
+	nbgpu::dfree(d_flags);
 	if (st != NBGPU_OK)
 		return st;
 	if (e != cudaSuccess) {
@@ -840,7 +840,7 @@ int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof, const
 	NB_ARG(d_F != nullptr && dof != nullptr && add != nullptr);
 	Context &c = ctx();
 	void *buf = nullptr;
-	NB_CUDA(cudaMalloc(&buf, (size_t)n * (sizeof(uint32_t) + sizeof(double))));
+	NB_CUDA(nbgpu::dmalloc(&buf, (size_t)n * (sizeof(uint32_t) + sizeof(double))));
 	double *d_add = (double *)buf;
 	uint32_t *d_dof = (uint32_t *)(d_add + n);
 	cudaError_t e = cudaMemcpyAsync(d_add, add, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream);
@@ -853,7 +853,7 @@ int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof, const
 	}
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(c.stream);
-	cudaFree(buf);
+	nbgpu::dfree(buf);
 	if (e != cudaSuccess) {
 		set_error("vector_add_entries: %s", cudaGetErrorString(e));
 		return NBGPU_ERR_CUDA;
@@ -876,7 +876,7 @@ int nbgpu_dirichlet_destroy(nbgpu_dirichlet_t *bc)
 		return NBGPU_OK;
 	if (ctx().ready && bc->buf) {
 		cudaStreamSynchronize(ctx().stream);
-		cudaFree(bc->buf);
+		nbgpu::dfree(bc->buf);
 	}
 	delete bc;
 	return NBGPU_OK;
@@ -908,7 +908,7 @@ int nbgpu_dirichlet_create(uint32_t N, uint32_t n, const uint32_t *dof, const do
 	bc->N = N;
 	bc->m = v_first.size();
 	const size_t m = bc->m;
-	cudaError_t e = cudaMalloc(&bc->buf, (size_t)N * sizeof(uint32_t) + 2 * m * sizeof(double) + 16);
+	cudaError_t e = nbgpu::dmalloc(&bc->buf, (size_t)N * sizeof(uint32_t) + 2 * m * sizeof(double) + 16);
 	double *d_first = (double *)bc->buf, *d_last = d_first + m;
 	uint32_t *d_order = (uint32_t *)(d_last + m);
 	if (e == cudaSuccess)
@@ -1004,7 +1004,7 @@ int nbgpu_gp_to_nodes(const nbgpu_mesh_t *m, const nbgpu_elem_tables_t *tables, 
 		return NBGPU_OK;
 	Context &c = ctx();
 	unsigned int *d_bad = nullptr;
-	NB_CUDA(cudaMalloc(&d_bad, sizeof(unsigned int)));
+	NB_CUDA(nbgpu::dmalloc(&d_bad, sizeof(unsigned int)));
 	cudaMemsetAsync(d_bad, 0xFF, sizeof(unsigned int), c.stream);
 	const size_t n = (size_t)m->N_nod * N_comp;
 	const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
@@ -1021,7 +1021,7 @@ int nbgpu_gp_to_nodes(const nbgpu_mesh_t *m, const nbgpu_elem_tables_t *tables, 
 		e = cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c.stream);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(c.stream);
-	cudaFree(d_bad);
+	nbgpu::dfree(d_bad);
 	if (e != cudaSuccess) {
 		set_error("gp_to_nodes: %s", cudaGetErrorString(e));
 		return NBGPU_ERR_CUDA;
@@ -1062,7 +1062,7 @@ int nbgpu_stress_from_strain(uint32_t N_elems, uint32_t N_gp, const double D[4],
 	Context &c = ctx();
 	uint8_t *d_en = nullptr;
 	if (enabled) {
-		NB_CUDA(cudaMalloc(&d_en, N_elems));
+		NB_CUDA(nbgpu::dmalloc(&d_en, N_elems));
 		NB_CUDA(cudaMemcpyAsync(d_en, enabled, N_elems, cudaMemcpyHostToDevice, c.stream));
 	}
 	const size_t n = (size_t)N_elems * N_gp;
@@ -1074,7 +1074,7 @@ int nbgpu_stress_from_strain(uint32_t N_elems, uint32_t N_gp, const double D[4],
 	if (e == cudaSuccess && d_en)
 		e = cudaStreamSynchronize(c.stream);
 	if (d_en)
-		cudaFree(d_en);
+		nbgpu::dfree(d_en);
 	if (e != cudaSuccess) {
 		set_error("stress_from_strain: %s", cudaGetErrorString(e));
 		return NBGPU_ERR_CUDA;

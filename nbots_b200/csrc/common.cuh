@@ -33,6 +33,7 @@ struct Context {
 	void *dev_state = nullptr;            // solver scalars (krylov.cu)
 	void *host_state = nullptr;           // pinned mirror
 	uint64_t launches = 0;
+	cudaMemPool_t pool = nullptr;         // retained allocation pool (null: plain cudaMalloc)
 };
 
 Context &ctx();
@@ -41,6 +42,20 @@ void set_error(const char *fmt, ...);
 // pinned staging buffer pair of at least `bytes` each
 int ensure_stage(size_t bytes);
 int ensure_workspace(size_t bytes);
+
+// Device memory from a RETAINED stream-ordered pool (cudaMallocAsync on the library's stream with the
+// release threshold at maximum): the reference's call pattern re-imports the matrix on every solver call,
+// and plain cudaMalloc / cudaFree of its 100+ MB blocks cost 1-160 ms each time (measured).  dmalloc
+// synchronises the stream, so the block is usable at once from any stream or blocking copy; dfree is
+// stream-ordered (everything that touched the block on another stream must have completed).
+// nbgpu_finalize returns the pool to the driver.  NBGPU_NO_POOL=1 falls back to cudaMalloc/cudaFree.
+cudaError_t dmalloc_bytes(void **p, size_t bytes);
+cudaError_t dfree(void *p);
+template <typename T>
+inline cudaError_t dmalloc(T **p, size_t bytes)
+{
+	return dmalloc_bytes(reinterpret_cast<void **>(p), bytes);
+}
 
 }  // namespace nbgpu
 

@@ -12,6 +12,36 @@ static Context g_ctx;
 
 Context &ctx() { return g_ctx; }
 
+cudaError_t dmalloc_bytes(void **p, size_t bytes)
+{
+	Context &c = g_ctx;
+	if (!bytes)
+		bytes = 1;
+	if (!c.pool)
+		return cudaMalloc(p, bytes);
+	cudaError_t e = cudaMallocAsync(p, bytes, c.stream);
+	if (e == cudaErrorMemoryAllocation) {
+		// blocks parked in the pool may be too fragmented for this request: give them back, retry
+		cudaGetLastError();
+		cudaStreamSynchronize(c.stream);
+		cudaMemPoolTrimTo(c.pool, 0);
+		e = cudaMallocAsync(p, bytes, c.stream);
+	}
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(c.stream);
+	return e;
+}
+
+cudaError_t dfree(void *p)
+{
+	Context &c = g_ctx;
+	if (!p)
+		return cudaSuccess;
+	if (!c.pool)
+		return cudaFree(p);
+	return cudaFreeAsync(p, c.stream);
+}
+
 void set_error(const char *fmt, ...)
 {
 	char buf[1024];
@@ -51,7 +81,20 @@ static int init_device(int device)
 	NB_CUDA(cudaEventCreate(&c.ev_b));
 	NB_CUDA(cudaEventCreateWithFlags(&c.ev_stage[0], cudaEventDisableTiming));
 	NB_CUDA(cudaEventCreateWithFlags(&c.ev_stage[1], cudaEventDisableTiming));
-	NB_CUDA(cudaMalloc(&c.partials, sizeof(double) * 4 * kMaxPartialBlocks));
+	c.pool = nullptr;
+	if (!getenv("NBGPU_NO_POOL")) {
+		int supported = 0;
+		cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, device);
+		if (supported && cudaDeviceGetDefaultMemPool(&c.pool, device) == cudaSuccess) {
+			uint64_t keep = UINT64_MAX;
+			if (cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
+				c.pool = nullptr;
+		} else {
+			c.pool = nullptr;
+		}
+		cudaGetLastError();
+	}
+	NB_CUDA(nbgpu::dmalloc(&c.partials, sizeof(double) * 4 * kMaxPartialBlocks));
 	c.ready = true;
 	return NBGPU_OK;
 }
@@ -92,10 +135,10 @@ int ensure_workspace(size_t bytes)
 		return NBGPU_OK;
 	NB_CUDA(cudaStreamSynchronize(c.stream));
 	if (c.ws)
-		NB_CUDA(cudaFree(c.ws));
+		NB_CUDA(nbgpu::dfree(c.ws));
 	c.ws = nullptr;
 	c.ws_bytes = 0;
-	cudaError_t e = cudaMalloc(&c.ws, bytes);
+	cudaError_t e = nbgpu::dmalloc(&c.ws, bytes);
 	if (e != cudaSuccess) {
 		set_error("workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
 		cudaGetLastError();
@@ -137,13 +180,18 @@ int nbgpu_finalize(void)
 		cudaEventDestroy(c.ev_stage[i]);
 	}
 	if (c.ws)
-		cudaFree(c.ws);
+		nbgpu::dfree(c.ws);
 	if (c.partials)
-		cudaFree(c.partials);
+		nbgpu::dfree(c.partials);
 	if (c.dev_state)
-		cudaFree(c.dev_state);
+		nbgpu::dfree(c.dev_state);
 	if (c.host_state)
 		cudaFreeHost(c.host_state);
+	if (c.pool) {
+		cudaStreamSynchronize(c.stream);
+		cudaMemPoolTrimTo(c.pool, 0);
+		c.pool = nullptr;
+	}
 	cudaEventDestroy(c.ev_a);
 	cudaEventDestroy(c.ev_b);
 	cudaStreamDestroy(c.stream);
@@ -208,9 +256,9 @@ int nbgpu_malloc(void **d_ptr, size_t bytes)
 {
 	NB_INIT();
 	NB_ARG(d_ptr != nullptr);
-	cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+	cudaError_t e = nbgpu::dmalloc(d_ptr, bytes ? bytes : 1);
 	if (e != cudaSuccess) {
-		set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+		set_error("nbgpu::dmalloc(%zu): %s", bytes, cudaGetErrorString(e));
 		cudaGetLastError();
 		return NBGPU_ERR_NOMEM;
 	}
@@ -222,7 +270,7 @@ int nbgpu_free(void *d_ptr)
 	NB_INIT();
 	if (d_ptr) {
 		NB_CUDA(cudaStreamSynchronize(g_ctx.stream));
-		NB_CUDA(cudaFree(d_ptr));
+		NB_CUDA(nbgpu::dfree(d_ptr));
 	}
 	return NBGPU_OK;
 }

@@ -468,7 +468,7 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 	double *xw = c.ws, *g = xw + Np, *p = g + Np, *w = p + Np;
 	double *q = jacobi ? w + Np : g, *diag = jacobi ? q + Np : nullptr;
 	if (!c.dev_state) {
-		NB_CUDA(cudaMalloc(&c.dev_state, sizeof(KrylovState)));
+		NB_CUDA(nbgpu::dmalloc(&c.dev_state, sizeof(KrylovState)));
 		NB_CUDA(cudaMallocHost(&c.host_state, 4 * sizeof(KrylovState)));
 		NB_CUDA(cudaEventCreateWithFlags(&g_poll_ev[0], cudaEventDisableTiming));
 		NB_CUDA(cudaEventCreateWithFlags(&g_poll_ev[1], cudaEventDisableTiming));

@@ -3,6 +3,7 @@
 // nb_sparse_create (sparse.c:20-60), nb_sparse_reset (sparse.c:127-132).
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 
 #include "matrix.cuh"
 
@@ -215,18 +216,33 @@ int upload_rows(T *d_dst, T *const *rows, const std::vector<uint64_t> &row_ptr)
 	});
 }
 
+// NBGPU_TRACE=1: wall-clock of the import steps on stderr (tuning aid)
+struct Trace {
+	bool on = getenv("NBGPU_TRACE") != nullptr;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	void lap(const char *what)
+	{
+		if (!on)
+			return;
+		auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[nbgpu] %-18s %8.3f ms\n", what,
+			std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
+
 struct DeviceTemp {
 	void *p = nullptr;
 	~DeviceTemp()
 	{
 		if (p)
-			cudaFree(p);
+			nbgpu::dfree(p);
 	}
 	int alloc(size_t bytes)
 	{
-		cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+		cudaError_t e = nbgpu::dmalloc(&p, bytes ? bytes : 1);
 		if (e != cudaSuccess) {
-			set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+			set_error("nbgpu::dmalloc(%zu): %s", bytes, cudaGetErrorString(e));
 			cudaGetLastError();
 			p = nullptr;
 			return NBGPU_ERR_NOMEM;
@@ -329,7 +345,7 @@ int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
 	}
 	off[A->n_slices] = (uint32_t)units;
 	A->stored = units * kSliceRows;
-	NB_CUDA(cudaMalloc(&A->d_slice_off, off.size() * sizeof(uint32_t)));
+	NB_CUDA(nbgpu::dmalloc(&A->d_slice_off, off.size() * sizeof(uint32_t)));
 	NB_CUDA(cudaMemcpyAsync(A->d_slice_off, off.data(), off.size() * sizeof(uint32_t),
 				cudaMemcpyHostToDevice, ctx().stream));
 	if (A->sigma > 1) {
@@ -337,15 +353,15 @@ int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
 		for (size_t pos = 0; pos < n_pos; pos++)
 			if (perm[pos] < N)
 				inv[perm[pos]] = (uint32_t)pos;
-		NB_CUDA(cudaMalloc(&A->d_perm, n_pos * sizeof(uint32_t)));
-		NB_CUDA(cudaMalloc(&A->d_inv_perm, (size_t)N * sizeof(uint32_t)));
+		NB_CUDA(nbgpu::dmalloc(&A->d_perm, n_pos * sizeof(uint32_t)));
+		NB_CUDA(nbgpu::dmalloc(&A->d_inv_perm, (size_t)N * sizeof(uint32_t)));
 		NB_CUDA(cudaMemcpy(A->d_perm, perm.data(), n_pos * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		NB_CUDA(cudaMemcpy(A->d_inv_perm, inv.data(), (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice));
 	}
 	NB_CUDA(cudaStreamSynchronize(ctx().stream));   // `off` goes out of scope
-	cudaError_t e = cudaMalloc(&A->d_val, std::max<size_t>(1, A->stored) * sizeof(double));
+	cudaError_t e = nbgpu::dmalloc(&A->d_val, std::max<size_t>(1, A->stored) * sizeof(double));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&A->d_col, std::max<size_t>(1, A->stored) * sizeof(uint32_t));
+		e = nbgpu::dmalloc(&A->d_col, std::max<size_t>(1, A->stored) * sizeof(uint32_t));
 	if (e != cudaSuccess) {
 		set_error("matrix of %llu stored entries: %s", (unsigned long long)A->stored,
 			  cudaGetErrorString(e));
@@ -390,7 +406,7 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 		NB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
 		NB_CUDA(cudaStreamSynchronize(c.stream));
 		if (!h_bad) {
-			NB_CUDA(cudaMalloc(&A->d_bcol, std::max<size_t>(1, A->stored / 4) * sizeof(uint32_t)));
+			NB_CUDA(nbgpu::dmalloc(&A->d_bcol, std::max<size_t>(1, A->stored / 4) * sizeof(uint32_t)));
 			build_bcol_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
 				A->n_slices, A->d_slice_off, A->d_col, A->d_bcol);
 			NB_LAUNCHED();
@@ -428,12 +444,12 @@ int nbgpu_matrix_destroy(nbgpu_matrix_t *A)
 	if (ctx().ready) {
 		cudaSetDevice(ctx().device);
 		cudaStreamSynchronize(ctx().stream);
-		cudaFree(A->d_slice_off);
-		cudaFree(A->d_val);
-		cudaFree(A->d_col);
-		cudaFree(A->d_bcol);
-		cudaFree(A->d_perm);
-		cudaFree(A->d_inv_perm);
+		nbgpu::dfree(A->d_slice_off);
+		nbgpu::dfree(A->d_val);
+		nbgpu::dfree(A->d_col);
+		nbgpu::dfree(A->d_bcol);
+		nbgpu::dfree(A->d_perm);
+		nbgpu::dfree(A->d_inv_perm);
 	}
 	delete A;
 	return NBGPU_OK;
@@ -499,18 +515,24 @@ int nbgpu_matrix_create_from_rows(uint32_t N, const uint32_t *rows_size, uint32_
 	NB_INIT();
 	NB_ARG(out != nullptr && (N == 0 || (rows_size != nullptr && rows_index != nullptr)));
 	nbgpu_matrix_t *A = new nbgpu_matrix_t();
+	Trace tr;
 	int st = build_layout(A, N, rows_size);
+	tr.lap("layout");
 	DeviceTemp dc, dv;
 	if (st == NBGPU_OK)
 		st = dc.alloc(A->nnz * sizeof(uint32_t));
 	if (st == NBGPU_OK && rows_values)
 		st = dv.alloc(A->nnz * sizeof(double));
+	tr.lap("temp alloc");
 	if (st == NBGPU_OK)
 		st = upload_rows<uint32_t>((uint32_t *)dc.p, rows_index, A->h_row_ptr);
+	tr.lap("upload cols");
 	if (st == NBGPU_OK && rows_values)
 		st = upload_rows<double>((double *)dv.p, rows_values, A->h_row_ptr);
+	tr.lap("upload vals");
 	if (st == NBGPU_OK)
 		st = convert_in(A, (const uint32_t *)dc.p, rows_values ? (const double *)dv.p : nullptr);
+	tr.lap("convert");
 	if (st != NBGPU_OK) {
 		nbgpu_matrix_destroy(A);
 		return st;

@@ -29,6 +29,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "nbgpu.h"
 
@@ -63,16 +64,30 @@ static void report(const char *who, int status)
 
 /* ----------------------------------------------------------- solver bot -- */
 
+static double now_ms(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
 static int solve(const nb_sparse_t *A, const double *b, double *x, uint32_t max_iter, double tolerance,
 		 uint32_t *niter_performed, double *tolerance_reached, int jacobi)
 {
 	nbgpu_matrix_t *M = NULL;
+	const int trace = getenv("NBGPU_TRACE") != NULL;
+	double t0 = now_ms();
 	int st = nbgpu_matrix_create_from_rows(A->N, A->rows_size, A->rows_index, A->rows_values, &M);
+	double t1 = now_ms();
 	if (st == NBGPU_OK)
 		st = jacobi ? nbgpu_pcg_jacobi_host(M, b, x, max_iter, tolerance, niter_performed,
 						    tolerance_reached)
 			    : nbgpu_cg_host(M, b, x, max_iter, tolerance, niter_performed, tolerance_reached);
+	double t2 = now_ms();
 	nbgpu_matrix_destroy(M);
+	if (trace)
+		fprintf(stderr, "[nbgpu shim] import %.3f ms, solve %.3f ms, release %.3f ms\n", t1 - t0, t2 - t1,
+			now_ms() - t2);
 	report(jacobi ? "nb_sparse_solve_CG_precond_Jacobi" : "nb_sparse_solve_conjugate_gradient", st);
 	return st;
 }
