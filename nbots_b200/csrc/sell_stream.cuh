@@ -234,7 +234,79 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		const double *sval = reinterpret_cast<const double *>(stage) + lane;
 		double acc = 0.0, diag = 0.0, x_row = 0.0;
 		bool have_row = false;
-		if (!BLOCKED) {
+		// every lane is done with the stage: hand it back to the producer
+		auto release = [&]() {
+			__syncwarp();
+			if (lane == 0) {
+				const uint64_t next = s64 + (uint64_t)cfg.stages * total_warps;
+				if (next < A.n_slices) {
+					fence_proxy_async();
+					issue(st, (uint32_t)next);
+				}
+			}
+		};
+		// A slice that fits one gather batch (all 2-D linear FEM rows, the 9-point stencil) is moved
+		// to registers as a whole while its gathers are in flight and the stage is re-armed BEFORE the
+		// arithmetic: the next bulk copy into this stage then overlaps gather latency and math, which
+		// keeps two copies per warp in flight instead of one (the kernel is bound by bytes in flight).
+		const bool single = (BLOCKED ? (width >> 1) : width) <= (uint32_t)kGatherBatch;
+		if (!BLOCKED && single) {
+			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + lane;
+			uint32_t cj[kGatherBatch];
+			double xj[kGatherBatch], vj[kGatherBatch];
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++)
+				cj[u] = (uint32_t)u < width ? scol[u * kSliceRows] : kPadCol;
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++)
+				xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? 0u : cj[u]));
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++)
+				vj[u] = (uint32_t)u < width ? sval[u * kSliceRows] : 0.0;
+			release();
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++) {
+				const double t = __dmul_rn(vj[u], xj[u]);
+				acc = (cj[u] == kPadCol) ? acc : __dadd_rn(acc, t);
+				if (cj[u] == row) {
+					diag = vj[u];
+					x_row = xj[u];
+					have_row = true;
+				}
+			}
+		} else if (BLOCKED && single) {
+			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + (lane >> 1);
+			const uint32_t nblk = width >> 1;
+			const uint32_t my_node = row >> 1;
+			uint32_t cb[kGatherBatch];
+			double2 xb[kGatherBatch];
+			double v0[kGatherBatch], v1[kGatherBatch];
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++)
+				cb[u] = (uint32_t)u < nblk ? scol[u * 16u] : kPadCol;
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++)
+				xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++) {
+				v0[u] = (uint32_t)u < nblk ? sval[(2 * u) * kSliceRows] : 0.0;
+				v1[u] = (uint32_t)u < nblk ? sval[(2 * u + 1) * kSliceRows] : 0.0;
+			}
+			release();
+#pragma unroll
+			for (int u = 0; u < kGatherBatch; u++) {
+				const bool pad = cb[u] == kPadCol;
+				const double t0 = __dmul_rn(v0[u], xb[u].x);
+				acc = pad ? acc : __dadd_rn(acc, t0);
+				const double t1 = __dmul_rn(v1[u], xb[u].y);
+				acc = pad ? acc : __dadd_rn(acc, t1);
+				if (cb[u] == my_node) {
+					diag = (row & 1) ? v1[u] : v0[u];
+					x_row = (row & 1) ? xb[u].y : xb[u].x;
+					have_row = true;
+				}
+			}
+		} else if (!BLOCKED) {
 			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + lane;
 			uint32_t j0 = 0;
 			// full batches: column ids, then ALL gathers, then (behind a warp barrier that
@@ -322,17 +394,10 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				}
 			}
 		}
+		if (!single)
+			release();
 		if (!have_row && row < A.N)
 			x_row = __ldg(x + row);   // row without a stored diagonal
-		// every lane is done with the stage: hand it back to the producer
-		__syncwarp();
-		if (lane == 0) {
-			const uint64_t next = s64 + (uint64_t)cfg.stages * total_warps;
-			if (next < A.n_slices) {
-				fence_proxy_async();
-				issue(st, (uint32_t)next);
-			}
-		}
 		body(row, acc, diag, x_row);
 	}
 }
