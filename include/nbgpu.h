@@ -97,10 +97,11 @@ int nbgpu_matrix_info(const nbgpu_matrix_t *A, uint32_t *N, uint64_t *nnz,
 		      uint32_t *n_slices, uint64_t *stored_entries);
 /* how the rows are stored: sigma = sorting window of the SELL-32-sigma layout
  * (1 = rows in natural order), uniform_width != 0 when every slice has that
- * width, blocked != 0 when the 2x2 node-block column ids are in use */
+ * width, blocked != 0 when the 2x2 node-block column ids are in use, idx16 != 0
+ * when the kernels read 16-bit column differences instead of 32-bit ids */
 int nbgpu_matrix_layout(const nbgpu_matrix_t *A, uint32_t *sigma,
 			uint32_t *uniform_width, uint32_t *max_width,
-			int *blocked);
+			int *blocked, int *idx16);
 int nbgpu_matrix_set_values_rows(nbgpu_matrix_t *A, double *const *rows_values);
 int nbgpu_matrix_set_values_csr(nbgpu_matrix_t *A, const double *vals);
 int nbgpu_matrix_get_values_rows(const nbgpu_matrix_t *A, double *const *rows_values);

@@ -94,9 +94,10 @@ class Matrix:
         N = C.c_uint32(); nnz = C.c_uint64(); ns = C.c_uint32(); st = C.c_uint64()
         check(lib().nbgpu_matrix_info(self.h, C.byref(N), C.byref(nnz), C.byref(ns), C.byref(st)))
         self.N, self.nnz, self.n_slices, self.stored = N.value, nnz.value, ns.value, st.value
-        sg = C.c_uint32(); uw = C.c_uint32(); mw = C.c_uint32(); bl = C.c_int()
-        check(lib().nbgpu_matrix_layout(self.h, C.byref(sg), C.byref(uw), C.byref(mw), C.byref(bl)))
+        sg = C.c_uint32(); uw = C.c_uint32(); mw = C.c_uint32(); bl = C.c_int(); i16 = C.c_int()
+        check(lib().nbgpu_matrix_layout(self.h, C.byref(sg), C.byref(uw), C.byref(mw), C.byref(bl), C.byref(i16)))
         self.sigma, self.uniform_width, self.max_width, self.blocked = sg.value, uw.value, mw.value, bool(bl.value)
+        self.idx16 = bool(i16.value)
 
     @classmethod
     def from_csr(cls, rows_size, cols, vals=None):

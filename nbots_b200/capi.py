@@ -69,7 +69,7 @@ SIGNATURES = {
     "nbgpu_matrix_create_from_csr": (C.c_int, [C.c_uint32, u32p, u32p, f64p, vpp]),
     "nbgpu_matrix_destroy": (C.c_int, [C.c_void_p]),
     "nbgpu_matrix_info": (C.c_int, [C.c_void_p, u32p, u64p, u32p, u64p]),
-    "nbgpu_matrix_layout": (C.c_int, [C.c_void_p, u32p, u32p, u32p, C.POINTER(C.c_int)]),
+    "nbgpu_matrix_layout": (C.c_int, [C.c_void_p, u32p, u32p, u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nbgpu_matrix_set_values_rows": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nbgpu_matrix_set_values_csr": (C.c_int, [C.c_void_p, f64p]),
     "nbgpu_matrix_get_values_rows": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -303,7 +303,7 @@ dist_init_kernel(SellView A, StreamConfig cfg, PeerTable T, unsigned long long s
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[2] = {0.0, 0.0};
 	bool ok = true;
-	sell_stream_rows<BLOCKED, JACOBI>(
+	sell_stream_rows<BLOCKED, JACOBI, false>(
 		A, x_ext, cfg, smem, [] { return true; },
 		[&] {
 			ok = warp_wait_halo(T, 1, seq);
@@ -363,7 +363,7 @@ dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[1] = {0.0};
 	bool active = true;
-	sell_stream_rows<BLOCKED, false>(
+	sell_stream_rows<BLOCKED, false, false>(
 		A, p_ext, cfg, smem,
 		[&] {
 			active = iteration_gate(k, st) && !*(volatile int *)&T.ctrl[T.rank]->error;
@@ -511,7 +511,7 @@ dist_plain_spmv_kernel(SellView A, StreamConfig cfg, PeerTable T, unsigned long 
 		       const double *__restrict__ x_ext, double *__restrict__ y, unsigned int *ticket)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	sell_stream_rows<BLOCKED, false>(
+	sell_stream_rows<BLOCKED, false, false>(
 		A, x_ext, cfg, smem, [] { return true; }, [&] { return warp_wait_halo(T, 1, seq); },
 		[&](uint32_t row, double acc, double, double) {
 			if (row < A.N)

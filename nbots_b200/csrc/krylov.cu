@@ -184,7 +184,7 @@ krylov_spmv_kernel(uint32_t k, uint32_t N, uint32_t n_slices, const uint32_t *__
 }
 
 // ---- streamed path: the matrix goes through shared memory (sell_stream.cuh) -----
-template <bool JACOBI, bool BLOCKED>
+template <bool JACOBI, int LAYOUT>   // LAYOUT = blocked | idx16 << 1
 __global__ void __launch_bounds__(kBlock, 2)
 krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ b,
 			  const double *__restrict__ x, double *__restrict__ g, double *__restrict__ p,
@@ -192,7 +192,7 @@ krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[2] = {0.0, 0.0};
-	sell_stream_rows<BLOCKED, JACOBI>(
+	sell_stream_rows<(LAYOUT & 1) != 0, JACOBI, (LAYOUT & 2) != 0>(
 		A, x, cfg, smem, [] { return true; }, [] { return true; },
 		[&](uint32_t row, double acc, double d, double) {
 			if (row < A.N)
@@ -201,7 +201,7 @@ krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict
 	init_finish<JACOBI>(dots, partials, st);
 }
 
-template <bool BLOCKED>
+template <int LAYOUT>
 __global__ void __launch_bounds__(kBlock, 2)
 krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, const double *__restrict__ p,
 			  double *__restrict__ w, double *partials, KrylovState *st)
@@ -209,7 +209,7 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, const double
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[1] = {0.0};
 	bool active = true;
-	sell_stream_rows<BLOCKED, false>(
+	sell_stream_rows<(LAYOUT & 1) != 0, false, (LAYOUT & 2) != 0>(
 		A, p, cfg, smem,
 		[&] {
 			// a function of (k, state) only: the whole grid takes the same branch
@@ -492,16 +492,18 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 	// streamed (TMA) path: same kernels, matrix staged through shared memory
 	SellView V;
 	V.N = N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
-	V.col = A->blocked ? A->d_bcol : A->d_col;
+	V.col = A->stream_ids();
 	V.uniform_width = A->uniform_width;
 	V.perm = A->d_perm;
 	StreamConfig scfg, icfg;
-	const void *sk = A->blocked ? (const void *)krylov_spmv_stream_kernel<true>
-				    : (const void *)krylov_spmv_stream_kernel<false>;
-	const void *ik = jacobi ? (A->blocked ? (const void *)krylov_init_stream_kernel<true, true>
-					      : (const void *)krylov_init_stream_kernel<true, false>)
-				: (A->blocked ? (const void *)krylov_init_stream_kernel<false, true>
-					      : (const void *)krylov_init_stream_kernel<false, false>);
+	const int layout = A->layout();
+	const void *sk = by_layout(layout, [](auto L) {
+		return (const void *)krylov_spmv_stream_kernel<decltype(L)::value>;
+	});
+	const void *ik = by_layout(layout, [&](auto L) {
+		return jacobi ? (const void *)krylov_init_stream_kernel<true, decltype(L)::value>
+			      : (const void *)krylov_init_stream_kernel<false, decltype(L)::value>;
+	});
 	const bool stream = stream_config(A, sk, &scfg) && stream_config(A, ik, &icfg);
 	const bool seq = g_seq_dots;
 	const bool pdl = !seq && !getenv("NBGPU_NO_PDL");
@@ -509,18 +511,13 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 
 	cudaError_t e;
 	if (stream) {
-		if (jacobi && A->blocked)
-			e = launch(false, krylov_init_stream_kernel<true, true>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
-				   xw, g, p, q, diag, partials, st);
-		else if (jacobi)
-			e = launch(false, krylov_init_stream_kernel<true, false>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
-				   xw, g, p, q, diag, partials, st);
-		else if (A->blocked)
-			e = launch(false, krylov_init_stream_kernel<false, true>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
-				   xw, g, p, q, diag, partials, st);
-		else
-			e = launch(false, krylov_init_stream_kernel<false, false>, icfg.grid, icfg.smem_bytes, V, icfg, d_b,
-				   xw, g, p, q, diag, partials, st);
+		e = by_layout(layout, [&](auto L) {
+			constexpr int kL = decltype(L)::value;
+			return jacobi ? launch(false, krylov_init_stream_kernel<true, kL>, icfg.grid, icfg.smem_bytes, V,
+					       icfg, d_b, xw, g, p, q, diag, partials, st)
+				      : launch(false, krylov_init_stream_kernel<false, kL>, icfg.grid, icfg.smem_bytes, V,
+					       icfg, d_b, xw, g, p, q, diag, partials, st);
+		});
 	} else if (jacobi) {
 		e = launch(false, krylov_init_kernel<true>, igrid, 0, N, A->n_slices, A->d_slice_off, A->d_perm, A->d_val, A->d_col,
 			   d_b, xw, g, p, q, diag, partials, st);
@@ -550,12 +547,11 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 			const bool prof = g_prof_on && k < kProfIters;
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k], c.stream));
-			if (stream && A->blocked)
-				e = launch(pdl, krylov_spmv_stream_kernel<true>, scfg.grid, scfg.smem_bytes, k, V, scfg, p, w,
-					   partials, st);
-			else if (stream)
-				e = launch(pdl, krylov_spmv_stream_kernel<false>, scfg.grid, scfg.smem_bytes, k, V, scfg, p, w,
-					   partials, st);
+			if (stream)
+				e = by_layout(layout, [&](auto L) {
+					return launch(pdl, krylov_spmv_stream_kernel<decltype(L)::value>, scfg.grid,
+						      scfg.smem_bytes, k, V, scfg, p, w, partials, st);
+				});
 			else
 				e = launch(pdl, krylov_spmv_kernel, sgrid, 0, k, N, A->n_slices, A->d_slice_off, A->d_perm, A->d_val,
 					   A->d_col, p, w, partials, st);

@@ -99,6 +99,50 @@ build_bcol_kernel(uint32_t n_slices, const uint32_t *__restrict__ slice_off,
 	}
 }
 
+// int16 differences of the column ids to the row's own index (per-block node ids to the row's node when
+// `blocked`), same positions as the source array; *too_far is raised when one does not fit.
+__global__ void __launch_bounds__(kBlock)
+build_idx16_kernel(bool blocked, uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
+		   const uint32_t *__restrict__ perm, const uint32_t *__restrict__ ids, short *__restrict__ out,
+		   int *too_far)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
+		const uint32_t off = slice_off[s], width = slice_off[s + 1] - off;
+		if (!blocked) {
+			const uint32_t row = perm ? perm[s * kSliceRows + lane] : s * kSliceRows + lane;
+			for (uint32_t j = 0; j < width; j++) {
+				const size_t idx = ((size_t)off + j) * kSliceRows + lane;
+				const uint32_t c = ids[idx];
+				int d = -32768;
+				if (c != kPadCol) {
+					const int64_t diff = (int64_t)c - (int64_t)row;
+					if (diff < -32767 || diff > 32767 || row >= N)
+						*too_far = 1;
+					d = (int)diff;
+				}
+				out[idx] = (short)d;
+			}
+		} else {
+			const uint32_t nl = lane & 15;
+			const uint32_t row = perm ? perm[s * kSliceRows + 2 * nl] : s * kSliceRows + 2 * nl;
+			for (uint32_t jb = lane >> 4; jb < (width >> 1); jb += 2) {
+				const size_t idx = ((size_t)(off >> 1) + jb) * 16u + nl;
+				const uint32_t c = ids[idx];
+				int d = -32768;
+				if (c != kPadCol) {
+					const int64_t diff = (int64_t)c - (int64_t)(row >> 1);
+					if (diff < -32767 || diff > 32767 || row >= N)
+						*too_far = 1;
+					d = (int)diff;
+				}
+				out[idx] = (short)d;
+			}
+		}
+	}
+}
+
 __global__ void __launch_bounds__(kBlock)
 sell_to_csr_kernel(uint32_t N, uint32_t n_slices, const uint64_t *__restrict__ row_ptr,
 		   const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ perm,
@@ -413,6 +457,22 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 			A->blocked = true;
 		}
 	}
+	if (d_cols && A->n_slices && !A->local_block && !getenv("NBGPU_NO_IDX16")) {
+		const size_t n_ids = A->blocked ? A->stored / 4 : A->stored;
+		NB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), c.stream));
+		NB_CUDA(nbgpu::dmalloc(&A->d_idx16, std::max<size_t>(1, n_ids) * sizeof(short)));
+		build_idx16_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
+			A->blocked, A->N, A->n_slices, A->d_slice_off, A->d_perm, A->blocked ? A->d_bcol : A->d_col,
+			A->d_idx16, (int *)bad.p);
+		NB_LAUNCHED();
+		NB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+		NB_CUDA(cudaStreamSynchronize(c.stream));
+		A->idx16 = !h_bad;
+		if (h_bad) {
+			nbgpu::dfree(A->d_idx16);
+			A->d_idx16 = nullptr;
+		}
+	}
 	return NBGPU_OK;
 }
 
@@ -448,6 +508,7 @@ int nbgpu_matrix_destroy(nbgpu_matrix_t *A)
 		nbgpu::dfree(A->d_val);
 		nbgpu::dfree(A->d_col);
 		nbgpu::dfree(A->d_bcol);
+		nbgpu::dfree(A->d_idx16);
 		nbgpu::dfree(A->d_perm);
 		nbgpu::dfree(A->d_inv_perm);
 	}
@@ -557,7 +618,7 @@ int nbgpu_matrix_info(const nbgpu_matrix_t *A, uint32_t *N, uint64_t *nnz, uint3
 }
 
 int nbgpu_matrix_layout(const nbgpu_matrix_t *A, uint32_t *sigma, uint32_t *uniform_width,
-			uint32_t *max_width, int *blocked)
+			uint32_t *max_width, int *blocked, int *idx16)
 {
 	NB_ARG(A != nullptr);
 	if (sigma)
@@ -568,6 +629,8 @@ int nbgpu_matrix_layout(const nbgpu_matrix_t *A, uint32_t *sigma, uint32_t *unif
 		*max_width = A->max_width;
 	if (blocked)
 		*blocked = A->blocked ? 1 : 0;
+	if (idx16)
+		*idx16 = A->idx16 ? 1 : 0;
 	return NBGPU_OK;
 }
 

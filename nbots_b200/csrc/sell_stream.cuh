@@ -94,21 +94,30 @@ constexpr int kGatherBatch = 9;                // gathers in flight per lane
 struct StreamConfig {
 	uint32_t cap;          // stage capacity in columns (>= widest slice)
 	uint32_t stages;       // ring depth per warp
-	uint32_t stage_bytes;  // cap * (256 + 128) or cap * (256 + 32) when blocked
+	uint32_t stage_bytes;  // cap * (256 + id bytes per column): ids are 128 / 32 (blocked) / 64 / 16 (16-bit)
 	uint32_t smem_bytes;   // dynamic shared memory per CTA
 	int grid;              // resident CTAs
 };
 
-__host__ __device__ inline uint32_t stream_stage_bytes(uint32_t cap, bool blocked)
+// bytes of column ids per stored entry-column of a slice
+__host__ __device__ constexpr uint32_t stream_id_bytes(bool blocked, bool idx16)
 {
-	return cap * (kSliceRows * 8u) + (blocked ? cap * 32u : cap * (kSliceRows * 4u));
+	return blocked ? (idx16 ? 16u : 32u) : (idx16 ? kSliceRows * 2u : kSliceRows * 4u);
 }
+
+__host__ __device__ inline uint32_t stream_stage_bytes(uint32_t cap, bool blocked, bool idx16)
+{
+	return cap * (kSliceRows * 8u) + cap * stream_id_bytes(blocked, idx16);
+}
+
+constexpr int kPadDelta = -32768;   // 16-bit column ids: padding marker (valid deltas are -32767 .. 32767)
 
 struct SellView {
 	uint32_t N, n_slices;
 	const uint32_t *slice_off;
 	const double *val;
-	const uint32_t *col;    // per-entry column ids, or per-block node ids when BLOCKED
+	const void *col;        // per-entry column ids, or per-block node ids when BLOCKED; uint32, or with
+				// IDX16 int16 differences to the row's own index (node index when BLOCKED)
 	// Visit order (rank-local blocks of a partitioned matrix): the v-th slice visited is
 	// (v + visit_shift) mod n_slices, so that the slices whose rows read halo columns come last,
 	// and `late()` -- the wait for the halo -- is only called before visit index late_from.
@@ -132,7 +141,7 @@ struct SellView {
 // false the warp only drains its in-flight copies and leaves.  `late()` is
 // called once, before the first slice with visit index >= A.late_from (slices
 // that need data a peer GPU is still sending); false = give up likewise.
-template <bool BLOCKED, bool WANT_DIAG, typename Gate, typename Late, typename Body>
+template <bool BLOCKED, bool WANT_DIAG, bool IDX16, typename Gate, typename Late, typename Body>
 __device__ __forceinline__ void sell_stream_rows(const SellView A, const double *__restrict__ x,
 						 const StreamConfig cfg, unsigned char *smem, Gate gate, Late late,
 						 Body body)
@@ -148,7 +157,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 						 kStreamWarps * kStreamMaxStages * sizeof(uint64_t)) +
 		      warp * kStreamMaxStages;
 	const uint32_t val_bytes_per_col = kSliceRows * 8u;
-	const uint32_t col_bytes_per_col = BLOCKED ? 32u : kSliceRows * 4u;
+	const uint32_t col_bytes_per_col = stream_id_bytes(BLOCKED, IDX16);
 
 	uint64_t policy = 0;
 	if (lane == 0) {
@@ -249,14 +258,25 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		// to registers as a whole while its gathers are in flight and the stage is re-armed BEFORE the
 		// arithmetic: the next bulk copy into this stage then overlaps gather latency and math, which
 		// keeps two copies per warp in flight instead of one (the kernel is bound by bytes in flight).
+		// id k of this lane: entry column k, or block k of the lane's node pair when BLOCKED
+		const unsigned char *sids = stage + (size_t)cfg.cap * val_bytes_per_col;
+		const uint32_t id_base = BLOCKED ? (row >> 1) : row;
+		auto load_id = [&](uint32_t k) -> uint32_t {
+			constexpr uint32_t kStride = BLOCKED ? 16u : kSliceRows;
+			const uint32_t mine = BLOCKED ? (lane >> 1) : lane;
+			if (IDX16) {
+				const int d = reinterpret_cast<const short *>(sids)[k * kStride + mine];
+				return d == kPadDelta ? kPadCol : id_base + (uint32_t)d;
+			}
+			return reinterpret_cast<const uint32_t *>(sids)[k * kStride + mine];
+		};
 		const bool single = (BLOCKED ? (width >> 1) : width) <= (uint32_t)kGatherBatch;
 		if (!BLOCKED && single) {
-			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + lane;
 			uint32_t cj[kGatherBatch];
 			double xj[kGatherBatch], vj[kGatherBatch];
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++)
-				cj[u] = (uint32_t)u < width ? scol[u * kSliceRows] : kPadCol;
+				cj[u] = (uint32_t)u < width ? load_id(u) : kPadCol;
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++)
 				xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? 0u : cj[u]));
@@ -275,7 +295,6 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				}
 			}
 		} else if (BLOCKED && single) {
-			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + (lane >> 1);
 			const uint32_t nblk = width >> 1;
 			const uint32_t my_node = row >> 1;
 			uint32_t cb[kGatherBatch];
@@ -283,7 +302,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			double v0[kGatherBatch], v1[kGatherBatch];
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++)
-				cb[u] = (uint32_t)u < nblk ? scol[u * 16u] : kPadCol;
+				cb[u] = (uint32_t)u < nblk ? load_id(u) : kPadCol;
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++)
 				xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
@@ -307,7 +326,6 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				}
 			}
 		} else if (!BLOCKED) {
-			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + lane;
 			uint32_t j0 = 0;
 			// full batches: column ids, then ALL gathers, then (behind a warp barrier that
 			// keeps the shared-memory value loads and hence the math from creeping up
@@ -317,7 +335,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				double xj[kGatherBatch];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					cj[u] = scol[(j0 + u) * kSliceRows];
+					cj[u] = load_id(j0 + u);
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
 					xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? 0u : cj[u]));
@@ -335,7 +353,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				}
 			}
 			for (; j0 < width; j0++) {
-				const uint32_t cj = scol[j0 * kSliceRows];
+				const uint32_t cj = load_id(j0);
 				const double v = sval[j0 * kSliceRows];
 				const double xj = ld_gather_f64(x + (cj == kPadCol ? 0u : cj));
 				const double t = __dmul_rn(v, xj);
@@ -348,7 +366,6 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			}
 		} else {
 			// one node id per 2x2 block; lanes 2k, 2k+1 (the two dofs of a node) share it
-			const uint32_t *scol = reinterpret_cast<const uint32_t *>(stage + (size_t)cfg.cap * val_bytes_per_col) + (lane >> 1);
 			const uint32_t nblk = width >> 1;
 			const uint32_t my_node = row >> 1;
 			uint32_t b0 = 0;
@@ -357,7 +374,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				double2 xb[kGatherBatch];
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					cb[u] = scol[(b0 + u) * 16u];
+					cb[u] = load_id(b0 + u);
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
 					xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
@@ -379,7 +396,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				}
 			}
 			for (; b0 < nblk; b0++) {
-				const uint32_t cb = scol[b0 * 16u];
+				const uint32_t cb = load_id(b0);
 				const double v0 = sval[(2 * b0) * kSliceRows], v1 = sval[(2 * b0 + 1) * kSliceRows];
 				const double2 xb = ld_gather_f64x2(x + 2 * (size_t)(cb == kPadCol ? 0u : cb));
 				const bool pad = cb == kPadCol;

@@ -27,12 +27,12 @@ spmv_sell_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ sli
 	}
 }
 
-template <bool BLOCKED>
+template <int LAYOUT>   // blocked | idx16 << 1
 __global__ void __launch_bounds__(kBlock, 2)
 spmv_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ x, double *__restrict__ y)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	sell_stream_rows<BLOCKED, false>(A, x, cfg, smem, [] { return true; }, [] { return true; }, [&](uint32_t row, double acc, double, double) {
+	sell_stream_rows<(LAYOUT & 1) != 0, false, (LAYOUT & 2) != 0>(A, x, cfg, smem, [] { return true; }, [] { return true; }, [&](uint32_t row, double acc, double, double) {
 		if (row < A.N)
 			y[row] = acc;
 	});
@@ -50,7 +50,7 @@ bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cf
 	if (A->max_width == 0)
 		return false;
 	const uint32_t cap = (A->max_width + 1u) & ~1u;
-	const uint32_t stage_bytes = stream_stage_bytes(cap, A->blocked);
+	const uint32_t stage_bytes = stream_stage_bytes(cap, A->blocked, A->idx16);
 	const uint32_t fixed = kStreamWarps * kStreamMaxStages * (sizeof(uint64_t) + sizeof(uint2));
 	int smem_optin = 0;
 	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx().device);
@@ -116,17 +116,19 @@ int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out)
 	if (A->N == 0)
 		return NBGPU_OK;
 	StreamConfig cfg;
-	const void *kernel = A->blocked ? (const void *)spmv_stream_kernel<true> : (const void *)spmv_stream_kernel<false>;
+	const void *kernel = by_layout(A->layout(), [](auto L) {
+		return (const void *)spmv_stream_kernel<decltype(L)::value>;
+	});
 	if (stream_config(A, kernel, &cfg)) {
 		SellView V;
 		V.N = A->N; V.n_slices = A->n_slices; V.slice_off = A->d_slice_off; V.val = A->d_val;
-		V.col = A->blocked ? A->d_bcol : A->d_col;
+		V.col = A->stream_ids();
 		V.uniform_width = A->uniform_width;
 		V.perm = A->d_perm;
-		if (A->blocked)
-			spmv_stream_kernel<true><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
-		else
-			spmv_stream_kernel<false><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
+		by_layout(A->layout(), [&](auto L) {
+			spmv_stream_kernel<decltype(L)::value><<<cfg.grid, kBlock, cfg.smem_bytes, ctx().stream>>>(V, cfg, d_in, d_out);
+			return 0;
+		});
 		NB_LAUNCHED();
 		return NBGPU_OK;
 	}

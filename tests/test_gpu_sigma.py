@@ -100,3 +100,57 @@ def test_large_irregular_triangle_mesh(nbgpu_lib, monkeypatch):
     assert np.array_equal(K.values_csr(), P.vals)
     x = meshgen.uniform_rhs(K.N)
     assert np.array_equal(K.spmv_host(x), P.spmv(x))
+
+
+# ---------------------------------------------------------------- 16-bit column ids --
+
+@pytest.mark.parametrize("name", TRIANGLE_CASES + ["quad_cantilever_64x16", "lap9_48"])
+@pytest.mark.parametrize("ids", ["16", "32"])
+def test_column_id_width_is_invisible(nbgpu_lib, monkeypatch, sequential_dots, name, ids):
+    if ids == "32":
+        monkeypatch.setenv("NBGPU_NO_IDX16", "1")
+    g = golden(name)
+    fem = "K_post" in g.files
+    A = api.Matrix.from_csr(g["rows_size"], g["cols"], g["K_post"] if fem else g["vals"])
+    assert A.idx16 == (ids == "16")
+    x, want = (g["x"], g["spmv_x"]) if fem else (g["b"], g["spmv_b"])
+    assert np.array_equal(A.spmv_host(x), want)
+    b = g["F_post"] if fem else g["b"]
+    st, sol, it, res = A.pcg_jacobi_host(b, tol=float(g["tol"]))
+    assert (st, it, res) == (int(g["pcg_status"]), int(g["pcg_iters"]), float(g["pcg_res"]))
+    assert np.array_equal(sol, g["x"])
+
+
+def test_far_columns_keep_32_bit_ids(nbgpu_lib, monkeypatch):
+    """Entries further than 32767 from the diagonal do not fit 16-bit differences: the matrix keeps its
+    32-bit ids (decided on the device at creation) and results stay exact."""
+    monkeypatch.delenv("NBGPU_NO_IDX16", raising=False)
+    rng = np.random.default_rng(9)
+    N = 70001
+    near = [np.unique(np.clip(i + rng.integers(-40, 41, 6), 0, N - 1)) for i in range(N)]
+    far_rows = set(rng.integers(0, N, 25).tolist())
+    rows = [np.unique(np.append(c, (i + 40000) % N)) if i in far_rows else c for i, c in enumerate(near)]
+    rs = np.array([r.size for r in rows], dtype=np.uint32)
+    cols = np.concatenate(rows).astype(np.uint32)
+    vals = rng.standard_normal(cols.size)
+    x = rng.standard_normal(N)
+    A = api.Matrix.from_csr(rs, cols, vals)
+    assert not A.idx16 and not A.blocked
+    assert np.array_equal(A.spmv_host(x), port.Csr(rs, cols, vals).spmv(x))
+    near_only = api.Matrix.from_csr(np.array([r.size for r in near], dtype=np.uint32),
+                                    np.concatenate(near).astype(np.uint32))
+    assert near_only.idx16
+    # the extreme differences that still fit: +-32767
+    N2 = 40000
+    rows = [np.unique([max(i - 32767, 0), i, min(i + 32767, N2 - 1)]) for i in range(N2)]
+    rs2 = np.array([r.size for r in rows], dtype=np.uint32)
+    c2 = np.concatenate(rows).astype(np.uint32)
+    v2 = rng.standard_normal(c2.size)
+    B = api.Matrix.from_csr(rs2, c2, v2)
+    x2 = rng.standard_normal(N2)
+    assert B.idx16
+    assert np.array_equal(B.spmv_host(x2), port.Csr(rs2, c2, v2).spmv(x2))
+    rows[5] = np.unique([5, 5 + 32768])
+    rs3 = np.array([r.size for r in rows], dtype=np.uint32)
+    c3 = np.concatenate(rows).astype(np.uint32)
+    assert not api.Matrix.from_csr(rs3, c3).idx16
