@@ -199,7 +199,7 @@ def run_ours(args):
     per = ms3 / max(1, n_prof.value)
     peak, peak_src = measured_peaks()
     bytes_spmv = 12 * nnz + 20 * N + 4          # SURVEY.md §8d, K1 (CSR-equivalent algorithmic bytes)
-    bytes_update, bytes_dir = 64 * N, 24 * N     # K2, K3
+    bytes_update, bytes_dir = 40 * N, 40 * N     # K2 (g, w, diag -> g, q), K3 (q, p, x -> p, x)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -215,7 +215,7 @@ def run_ours(args):
                                              "GB/s": round(bytes_update / (per[1] * 1e-3) / 1e9, 1)},
                     "krylov_dir_kernel": {"ms": round(float(per[2]), 5),
                                           "GB/s": round(bytes_dir / (per[2] * 1e-3) / 1e9, 1)}},
-                "iteration_bytes_model": 12 * nnz + 108 * N,
+                "iteration_bytes_model": 12 * nnz + 108 * N,   # SURVEY §8d model (the kernels move 100 N of vectors)
                 "iteration_GBps": round((12 * nnz + 108 * N) * iters / (ms_step * 1e-3) / 1e9, 1)}
 
     # ---- e2e: the reference-facing call with host buffers --------------------------------------------

@@ -228,23 +228,22 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, const double
 	spmv_finish(dots, partials, st);
 }
 
-// K2: x += a p, g += a w, q = g / diag, gq' = g.q, gg' = g.g   (:59-68)
+// K2: g += a w, q = g / diag, gq' = g.q, gg' = g.g   (:64-68; x += a p is done by K3)
 // Two elements per thread and trip, every load of a trip issued before the first
-// use; the first trip's p, x, g, diag are loaded before the dependency wait (the
+// use; the first trip's g, diag are loaded before the dependency wait (the
 // SpMV kernel running ahead of us only writes w and the scalars).
 template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock)
-krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const double *__restrict__ w,
-		     const double *__restrict__ diag, double *__restrict__ x, double *__restrict__ g,
-		     double *__restrict__ q, double *partials, KrylovState *st)
+krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ w, const double *__restrict__ diag,
+		     double *__restrict__ g, double *__restrict__ q, double *partials, KrylovState *st)
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
-	double p0 = 0, x0 = 0, g0 = 0, d0 = 1, p1 = 0, x1 = 0, g1 = 0, d1 = 1;
+	double g0 = 0, d0 = 1, g1 = 0, d1 = 1;
 	if (base < N) {
 		const uint32_t j1 = base + stride < N ? base + stride : base;
-		p0 = p[base]; x0 = x[base]; g0 = g[base];
-		p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+		g0 = g[base];
+		g1 = g[j1];
 		if (JACOBI) {
 			d0 = diag[base];
 			d1 = diag[j1];
@@ -261,8 +260,8 @@ krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
 		if (i0 != base) {
-			p0 = p[i0]; x0 = x[i0]; g0 = g[i0];
-			p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+			g0 = g[i0];
+			g1 = g[j1];
 			if (JACOBI) {
 				d0 = diag[i0];
 				d1 = diag[j1];
@@ -271,7 +270,6 @@ krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const
 		const double w0 = w[i0], w1 = w[j1];
 		const double gn0 = __dadd_rn(g0, __dmul_rn(alpha, w0));
 		const double gn1 = __dadd_rn(g1, __dmul_rn(alpha, w1));
-		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
 		g[i0] = gn0;
 		dots[0] = __dadd_rn(dots[0], __dmul_rn(gn0, gn0));
 		if (JACOBI) {
@@ -280,7 +278,6 @@ krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const
 			dots[1] = __dadd_rn(dots[1], __dmul_rn(gn0, q0));
 		}
 		if (has1) {
-			x[i1] = __dadd_rn(x1, __dmul_rn(alpha, p1));
 			g[i1] = gn1;
 			dots[0] = __dadd_rn(dots[0], __dmul_rn(gn1, gn1));
 			if (JACOBI) {
@@ -299,23 +296,28 @@ krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ p, const
 	}
 }
 
-// K3: p = -q + b p   (:70-74); plain CG passes q == g.  p is preloaded before the
-// dependency wait (the update kernel ahead of us does not write it).
+// K3: x += a p (:62-63, moved here from K2: p is read once per iteration instead of twice; same
+// operations, same rounding), then p = -q + b p (:70-74); plain CG passes q == g.  p and x are
+// preloaded before the dependency wait (the update kernel ahead of us writes neither).
 __global__ void __launch_bounds__(kBlock)
 krylov_dir_kernel(uint32_t k, uint32_t N, const double *__restrict__ q, double *__restrict__ p,
-		  const KrylovState *st)
+		  double *__restrict__ x, const KrylovState *st)
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
-	double p0 = 0, p1 = 0;
+	double p0 = 0, p1 = 0, x0 = 0, x1 = 0;
 	if (base < N) {
+		const uint32_t j1 = base + stride < N ? base + stride : base;
 		p0 = p[base];
-		p1 = p[base + stride < N ? base + stride : base];
+		p1 = p[j1];
+		x0 = x[base];
+		x1 = x[j1];
 	}
 	pdl_wait();
 	pdl_launch_dependents();
 	if (*(volatile const int32_t *)&st->done)
 		return;
+	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);
 	const double beta = __ddiv_rn(st->gq[(k + 1) & 1], st->gq[k & 1]);
 	for (uint32_t i0 = base; i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
@@ -324,11 +326,16 @@ krylov_dir_kernel(uint32_t k, uint32_t N, const double *__restrict__ q, double *
 		if (i0 != base) {
 			p0 = p[i0];
 			p1 = p[j1];
+			x0 = x[i0];
+			x1 = x[j1];
 		}
 		const double q0 = q[i0], q1 = q[j1];
+		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
 		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, p0));
-		if (has1)
+		if (has1) {
+			x[i1] = __dadd_rn(x1, __dmul_rn(alpha, p1));
 			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
+		}
 	}
 }
 
@@ -563,9 +570,9 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 1], c.stream));
 			if (jacobi)
-				e = launch(pdl, krylov_update_kernel<true>, ugrid, 0, k, N, p, w, diag, xw, g, q, partials, st);
+				e = launch(pdl, krylov_update_kernel<true>, ugrid, 0, k, N, w, diag, g, q, partials, st);
 			else
-				e = launch(pdl, krylov_update_kernel<false>, ugrid, 0, k, N, p, w, diag, xw, g, q, partials, st);
+				e = launch(pdl, krylov_update_kernel<false>, ugrid, 0, k, N, w, diag, g, q, partials, st);
 			NB_CUDA(e);
 			if (seq) {
 				seq_dot_kernel<<<1, 32, 0, c.stream>>>(N, g, g, &st->gg[(k + 1) % 3u], jacobi ? g : nullptr,
@@ -574,7 +581,7 @@ int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t
 			}
 			if (prof)
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 2], c.stream));
-			NB_CUDA(launch(pdl, krylov_dir_kernel, dgrid, 0, k, N, q, p, st));
+			NB_CUDA(launch(pdl, krylov_dir_kernel, dgrid, 0, k, N, q, p, xw, st));
 			if (prof) {
 				NB_CUDA(cudaEventRecord(g_prof_ev[4 * k + 3], c.stream));
 				g_prof_recorded = k + 1;
