@@ -397,17 +397,17 @@ dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned
 // ---- K2: waits for all p.w, update, posts the partial (g.g, g.q) --------------------
 template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock)
-dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, const double *__restrict__ p,
-		   const double *__restrict__ w, const double *__restrict__ diag, double *__restrict__ x,
+dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
+		   const double *__restrict__ w, const double *__restrict__ diag,
 		   double *__restrict__ g, double *__restrict__ q, double *partials, DistState *st)
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const uint32_t base_i = blockIdx.x * blockDim.x + threadIdx.x;
-	double p0 = 0, x0 = 0, g0 = 0, d0 = 1, p1 = 0, x1 = 0, g1 = 0, d1 = 1;
+	double g0 = 0, d0 = 1, g1 = 0, d1 = 1;
 	if (base_i < N) {
 		const uint32_t j1 = base_i + stride < N ? base_i + stride : base_i;
-		p0 = p[base_i]; x0 = x[base_i]; g0 = g[base_i];
-		p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+		g0 = g[base_i];
+		g1 = g[j1];
 		if (JACOBI) {
 			d0 = diag[base_i];
 			d1 = diag[j1];
@@ -430,8 +430,8 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
 		if (i0 != base_i) {
-			p0 = p[i0]; x0 = x[i0]; g0 = g[i0];
-			p1 = p[j1]; x1 = x[j1]; g1 = g[j1];
+			g0 = g[i0];
+			g1 = g[j1];
 			if (JACOBI) {
 				d0 = diag[i0];
 				d1 = diag[j1];
@@ -440,7 +440,6 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		const double w0 = w[i0], w1 = w[j1];
 		const double gn0 = __dadd_rn(g0, __dmul_rn(alpha, w0));
 		const double gn1 = __dadd_rn(g1, __dmul_rn(alpha, w1));
-		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
 		g[i0] = gn0;
 		dots[0] = __dadd_rn(dots[0], __dmul_rn(gn0, gn0));
 		if (JACOBI) {
@@ -449,7 +448,6 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 			dots[1] = __dadd_rn(dots[1], __dmul_rn(gn0, q0));
 		}
 		if (has1) {
-			x[i1] = __dadd_rn(x1, __dmul_rn(alpha, p1));
 			g[i1] = gn1;
 			dots[0] = __dadd_rn(dots[0], __dmul_rn(gn1, gn1));
 			if (JACOBI) {
@@ -464,17 +462,20 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		post_gq(T, tot[0], JACOBI ? tot[1] : tot[0], base + k + 2);
 }
 
-// ---- K3: waits for all (g.g, g.q), p = -q + beta p ---------------------------------
+// ---- K3: waits for all (g.g, g.q), x += alpha p, p = -q + beta p --------------------
 __global__ void __launch_bounds__(kBlock)
 dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, const double *__restrict__ q,
-		double *__restrict__ p, DistState *st)
+		double *__restrict__ p, double *__restrict__ x, DistState *st)
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const uint32_t base_i = blockIdx.x * blockDim.x + threadIdx.x;
-	double p0 = 0, p1 = 0;
+	double p0 = 0, p1 = 0, x0 = 0, x1 = 0;
 	if (base_i < N) {
+		const uint32_t j1 = base_i + stride < N ? base_i + stride : base_i;
 		p0 = p[base_i];
-		p1 = p[base_i + stride < N ? base_i + stride : base_i];
+		p1 = p[j1];
+		x0 = x[base_i];
+		x1 = x[j1];
 	}
 	pdl_wait();
 	pdl_launch_dependents();
@@ -485,6 +486,7 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 		return;
 	const double gg = tot[0], gq = tot[1];
 	const double beta = __ddiv_rn(gq, st->gq[k & 1]);
+	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);   // the update kernel stored pw
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		st->gg[(k + 1) % 3u] = gg;
 		st->gq[(k + 1) & 1] = gq;
@@ -496,11 +498,16 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 		if (i0 != base_i) {
 			p0 = p[i0];
 			p1 = p[j1];
+			x0 = x[i0];
+			x1 = x[j1];
 		}
 		const double q0 = q[i0], q1 = q[j1];
+		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
 		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, p0));
-		if (has1)
+		if (has1) {
+			x[i1] = __dadd_rn(x1, __dmul_rn(alpha, p1));
 			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
+		}
 	}
 }
 
@@ -963,13 +970,13 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 					   (const uint32_t *)P->d_send_idx, (const double *)p, w, c.partials, st);
 			NB_CUDA(e);
 			if (jacobi)
-				e = launch(pdl, dist_update_kernel<true>, ugrid, kBlock, 0, k, N, T, base, (const double *)p, w,
-					   diag, xw, g, q, c.partials, st);
+				e = launch(pdl, dist_update_kernel<true>, ugrid, kBlock, 0, k, N, T, base, (const double *)w,
+					   (const double *)diag, g, q, c.partials, st);
 			else
-				e = launch(pdl, dist_update_kernel<false>, ugrid, kBlock, 0, k, N, T, base, (const double *)p, w,
-					   diag, xw, g, q, c.partials, st);
+				e = launch(pdl, dist_update_kernel<false>, ugrid, kBlock, 0, k, N, T, base, (const double *)w,
+					   (const double *)diag, g, q, c.partials, st);
 			NB_CUDA(e);
-			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p, st));
+			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p, xw, st));
 		}
 		if (k == max_iter) {
 			if (A->blocked)
