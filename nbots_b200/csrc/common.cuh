@@ -43,6 +43,10 @@ void set_error(const char *fmt, ...);
 int ensure_stage(size_t bytes);
 int ensure_workspace(size_t bytes);
 
+// L2 residency control for a solve (context.cu)
+bool l2_pin(void *ptr, size_t bytes, bool others_streaming);
+void l2_unpin();
+
 // Device memory from a RETAINED stream-ordered pool (cudaMallocAsync on the library's stream with the
 // release threshold at maximum): the reference's call pattern re-imports the matrix on every solver call,
 // and plain cudaMalloc / cudaFree of its 100+ MB blocks cost 1-160 ms each time (measured).  dmalloc

@@ -148,6 +148,49 @@ int ensure_workspace(size_t bytes)
 	return NBGPU_OK;
 }
 
+// Pin [ptr, ptr+bytes) in the persisting-L2 carve-out for kernels on the stream; everything else is
+// marked streaming (`others_streaming`) or left to the normal policy.  Returns whether a window was
+// installed.
+bool l2_pin(void *ptr, size_t bytes, bool others_streaming)
+{
+	if (getenv("NBGPU_NO_L2_PIN"))
+		return false;
+	Context &c = ctx();
+	int max_persist = 0, max_window = 0;
+	cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
+	cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
+	if (max_persist <= 0 || max_window <= 0 || bytes == 0 || bytes > (size_t)max_window ||
+	    bytes > (size_t)max_persist)
+		return false;   // vectors larger than the carve-out: leave the L2 to its own policy
+	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	v.accessPolicyWindow.base_ptr = ptr;
+	v.accessPolicyWindow.num_bytes = bytes;
+	v.accessPolicyWindow.hitRatio = 1.0f;
+	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	v.accessPolicyWindow.missProp = others_streaming ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+	if (cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return true;
+}
+
+void l2_unpin()
+{
+	Context &c = ctx();
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	v.accessPolicyWindow.num_bytes = 0;
+	cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &v);
+	cudaCtxResetPersistingL2Cache();
+	cudaGetLastError();
+}
+
 }  // namespace nbgpu
 
 using namespace nbgpu;

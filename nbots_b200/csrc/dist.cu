@@ -899,6 +899,8 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 	double *xw = c.ws, *g = xw + Np, *w = g + Np;
 	double *q = jacobi ? w + Np : g, *diag = jacobi ? q + Np : nullptr;
 	double *p = D->p_ext(), *x_ext = D->x_ext();
+	// No persisting-L2 window here: with p in the IPC window (outside the work-vector block) a window
+	// over the other vectors measured SLOWER than the default policy (51.2 vs 49.6 us/iteration, 1 M dof).
 	DistState *st = D->d_state, *hst = D->h_state;
 	int *herr = (int *)(hst + 4);   // pinned, behind the four state slots
 	herr[0] = herr[1] = herr[2] = 0;

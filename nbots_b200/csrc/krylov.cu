@@ -421,48 +421,6 @@ uint32_t g_prof_recorded = 0;
 double g_prof_ms[3] = {0, 0, 0};
 uint32_t g_prof_n = 0;
 
-// Pin [ptr, ptr+bytes) in the persisting-L2 carve-out for kernels on the stream,
-// mark everything else streaming.  Returns whether a window was installed.
-bool l2_pin(void *ptr, size_t bytes)
-{
-	if (getenv("NBGPU_NO_L2_PIN"))
-		return false;
-	Context &c = ctx();
-	int max_persist = 0, max_window = 0;
-	cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
-	cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
-	if (max_persist <= 0 || max_window <= 0 || bytes == 0 || bytes > (size_t)max_window ||
-	    bytes > (size_t)max_persist)
-		return false;   // vectors larger than the carve-out: leave the L2 to its own policy
-	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) {
-		cudaGetLastError();
-		return false;
-	}
-	cudaStreamAttrValue v;
-	memset(&v, 0, sizeof(v));
-	v.accessPolicyWindow.base_ptr = ptr;
-	v.accessPolicyWindow.num_bytes = bytes;
-	v.accessPolicyWindow.hitRatio = 1.0f;
-	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-	v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-	if (cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
-		cudaGetLastError();
-		return false;
-	}
-	return true;
-}
-
-void l2_unpin()
-{
-	Context &c = ctx();
-	cudaStreamAttrValue v;
-	memset(&v, 0, sizeof(v));
-	v.accessPolicyWindow.num_bytes = 0;
-	cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &v);
-	cudaCtxResetPersistingL2Cache();
-	cudaGetLastError();
-}
-
 int solve_impl(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_iter, double tol,
 	       uint32_t *niter, double *tol_reached, bool jacobi)
 {
@@ -647,7 +605,7 @@ int solve(const nbgpu_matrix_t *A, const double *d_b, double *d_x, uint32_t max_
 	const size_t Np = ((size_t)A->N + 1) & ~(size_t)1;
 	const size_t ws_bytes = (jacobi ? 6 : 4) * Np * sizeof(double);
 	NB_TRY(ensure_workspace(ws_bytes));
-	const bool pinned = l2_pin(ctx().ws, ws_bytes);
+	const bool pinned = l2_pin(ctx().ws, ws_bytes, true);
 	const int status = solve_impl(A, d_b, d_x, max_iter, tol, niter, tol_reached, jacobi);
 	if (pinned)
 		l2_unpin();
