@@ -24,6 +24,7 @@
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <pthread.h>
 #include <stdbool.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -64,6 +65,13 @@ static void report(const char *who, int status)
 
 /* ----------------------------------------------------------- solver bot -- */
 
+/* The reference entry points are re-entrant (no global state); the device library has one context, one
+ * stream and one set of work vectors per process.  Calls arriving from several host threads are therefore
+ * serialised here -- each still runs on the whole GPU. */
+static pthread_mutex_t g_entry_lock = PTHREAD_MUTEX_INITIALIZER;
+#define ENTER() pthread_mutex_lock(&g_entry_lock)
+#define LEAVE() pthread_mutex_unlock(&g_entry_lock)
+
 static double now_ms(void)
 {
 	struct timespec t;
@@ -76,6 +84,7 @@ static int solve(const nb_sparse_t *A, const double *b, double *x, uint32_t max_
 {
 	nbgpu_matrix_t *M = NULL;
 	const int trace = getenv("NBGPU_TRACE") != NULL;
+	ENTER();
 	double t0 = now_ms();
 	int st = nbgpu_matrix_create_from_rows(A->N, A->rows_size, A->rows_index, A->rows_values, &M);
 	double t1 = now_ms();
@@ -89,6 +98,7 @@ static int solve(const nb_sparse_t *A, const double *b, double *x, uint32_t max_
 		fprintf(stderr, "[nbgpu shim] import %.3f ms, solve %.3f ms, release %.3f ms\n", t1 - t0, t2 - t1,
 			now_ms() - t2);
 	report(jacobi ? "nb_sparse_solve_CG_precond_Jacobi" : "nb_sparse_solve_conjugate_gradient", st);
+	LEAVE();
 	return st;
 }
 
@@ -115,10 +125,12 @@ void nb_sparse_multiply_vector(const nb_sparse_t *A, const double *in, double *o
 {
 	(void)omp_parallel_threads;
 	nbgpu_matrix_t *M = NULL;
+	ENTER();
 	int st = nbgpu_matrix_create_from_rows(A->N, A->rows_size, A->rows_index, A->rows_values, &M);
 	if (st == NBGPU_OK)
 		st = nbgpu_spmv_host(M, in, out);
 	nbgpu_matrix_destroy(M);
+	LEAVE();
 	if (st != NBGPU_OK) {
 		/* the reference signature is void: a device failure cannot be reported, so it is fatal */
 		report("nb_sparse_multiply_vector", st);
@@ -308,7 +320,9 @@ int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh
 			     bool enable_self_weight, double gravity[2], nb_analysis2D_t analysis2D,
 			     nb_analysis2D_params *params2D, const bool *elements_enabled)
 {
+	ENTER();
 	resolve();
+	LEAVE();
 	if (M != NULL) {
 		/* the lumped mass vector belongs to the dynamic drivers, outside this hot path */
 		fprintf(stderr, "nbots_b200: pipeline_assemble_system with a mass vector is not accelerated\n");
@@ -322,6 +336,7 @@ int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh
 	double *d_F = NULL;
 	int status = 1;
 	int st = flatten_mesh(part, tab.N_nodes, 0, &fm);
+	ENTER();
 	if (st == NBGPU_OK)
 		st = nbgpu_matrix_create_from_rows(K->N, K->rows_size, K->rows_index, NULL, &dK);
 	if (st == NBGPU_OK)
@@ -355,6 +370,7 @@ int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh
 	nbgpu_free(d_F);
 	nbgpu_mesh_destroy(dmesh);
 	nbgpu_matrix_destroy(dK);
+	LEAVE();
 	free_mesh(&fm);
 	report("pipeline_assemble_system", st);
 	return st != NBGPU_OK ? st : status;
@@ -365,6 +381,7 @@ int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh
 int nb_fem_interpolate_from_gpoints_to_nodes(const nb_mesh2D_t *const part, const nb_fem_elem_t *const elem,
 					     uint32_t N_comp, const double *gp_values, double *nodal_values)
 {
+	ENTER();
 	resolve();
 	nbgpu_elem_tables_t tab;
 	read_tables(elem, &tab);
@@ -395,6 +412,7 @@ int nb_fem_interpolate_from_gpoints_to_nodes(const nb_mesh2D_t *const part, cons
 	nbgpu_free(d_gp);
 	nbgpu_free(d_nod);
 	nbgpu_mesh_destroy(dmesh);
+	LEAVE();
 	free_mesh(&fm);
 	report("nb_fem_interpolate_from_gpoints_to_nodes", st);
 	return st != NBGPU_OK ? st : status;
@@ -508,7 +526,9 @@ int nb_fem_compute_2D_Solid_Mechanics(const nb_mesh2D_t *const part, const nb_fe
 				      nb_analysis2D_params *params2D, const bool *elements_enabled,
 				      double *displacement, double *strain)
 {
+	ENTER();
 	resolve();
+	LEAVE();
 	nbgpu_elem_tables_t tab;
 	read_tables(elemtype, &tab);
 	flat_mesh_t fm;
@@ -519,11 +539,13 @@ int nb_fem_compute_2D_Solid_Mechanics(const nb_mesh2D_t *const part, const nb_fe
 		/* the reference's own constitutive matrix (formulas.c:32-46) */
 		double D[4];
 		R.constitutive(D, material, analysis2D);
+		ENTER();
 		st = nbgpu_fem_static_elasticity2d_lists(&fm.d, &tab, D, R.mat_density(material), neu.n,
 							 neu.dof, neu.val, dir.n, dir.dof, dir.val,
 							 enable_self_weight, gravity, analysis2D,
 							 params2D->thickness, (const uint8_t *)elements_enabled,
 							 NBGPU_ASSEMBLY_GATHER, 0.0, displacement, strain, NULL);
+		LEAVE();
 	}
 	free(neu.dof); free(neu.val); free(dir.dof); free(dir.val);
 	free_mesh(&fm);

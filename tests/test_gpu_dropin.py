@@ -76,3 +76,57 @@ SCRIPT = textwrap.dedent('''
 def test_reference_call_sites_run_on_the_device(nbgpu_lib):
     out = subprocess.run([sys.executable, "-c", SCRIPT % ROOT], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DROPIN_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_shim_entry_points_tolerate_concurrent_callers(nbgpu_lib):
+    """The reference's solver entry points are re-entrant; the shim serialises callers that arrive from
+    several host threads (one device context per process) instead of corrupting its work vectors."""
+    import ctypes as C
+    import threading
+
+    import numpy as np
+
+    import bench
+    from nbots_b200 import capi
+    from util import golden
+
+    shim = C.CDLL(capi.SHIM_PATH)
+    pcg = shim.nb_sparse_solve_CG_precond_Jacobi
+    pcg.restype = C.c_int
+    pcg.argtypes = [C.POINTER(bench.NbSparse), capi.f64p, capi.f64p, C.c_uint32, C.c_double, capi.u32p, capi.f64p,
+                    C.c_uint32]
+    mv = shim.nb_sparse_multiply_vector
+    mv.restype = None
+    mv.argtypes = [C.POINTER(bench.NbSparse), capi.f64p, capi.f64p, C.c_uint32]
+    cases = []
+    for name in ("quad_cantilever_64x16", "plate_with_hole_trg1000", "quad_void_selfweight_24x8"):
+        g = golden(name)
+        rs, cols, vals = g["rows_size"].copy(), g["cols"].copy(), g["K_post"].copy()
+        A, keep = bench.host_nb_sparse(rs, cols, vals)
+        cases.append((g, A, keep, rs, cols, vals))
+    errors = []
+
+    def worker(idx):
+        g, A, keep, rs, cols, vals = cases[idx % len(cases)]
+        b = np.ascontiguousarray(g["F_post"])
+        tol = 1e-8 * float(np.linalg.norm(b))
+        try:
+            for _ in range(6):
+                x = np.zeros(rs.size)
+                it = C.c_uint32(0)
+                res = C.c_double(0)
+                st = pcg(C.byref(A), b.ctypes.data_as(capi.f64p), x.ctypes.data_as(capi.f64p), rs.size, tol,
+                         C.byref(it), C.byref(res), 1)
+                y = np.zeros(rs.size)
+                mv(C.byref(A), x.ctypes.data_as(capi.f64p), y.ctypes.data_as(capi.f64p), 1)
+                if st != 0 or np.linalg.norm(y - b) > 2 * tol:
+                    errors.append((idx, st, float(np.linalg.norm(y - b)), tol))
+        except Exception as e:                       # pragma: no cover
+            errors.append((idx, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
