@@ -1,0 +1,105 @@
+"""GPU parity at BASELINE.json's full single-GPU size (configs[1]: 1000 x 500 quads, 1 003 002 dof,
+18 018 004 stored entries), checked against the port where the port finishes in seconds and through
+size-independent properties where it does not: closed-form counts, symmetry, linearity, true residual,
+energy.  One module-scoped system keeps the cost to one import + one assembly."""
+import os
+
+import numpy as np
+import pytest
+
+import bench
+from nbots_b200 import api, capi, meshgen
+from oracle import port
+from util import flatten_bcs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def q1(nbgpu_lib):
+    m = bench.workload_mesh(1)
+    rs, cols = api.pattern_from_mesh(m)
+    K = api.Matrix.from_csr(rs, cols)
+    mesh = api.Mesh(m)
+    d_F = api.DeviceBuffer.zeros(K.N)
+    st, _ = mesh.assemble(K, d_F, bench.E_MOD, bench.POISSON, thickness=bench.THICKNESS)
+    assert st == 0
+    # the port's system, same steps (pattern: port, ~1 s; assembly 500 k quads: ~1.5 s)
+    prs, pcols = port.pattern_from_mesh(m)
+    P = port.Csr(prs, pcols)
+    pst, F = port.assemble(P, m, bench.E_MOD, bench.POISSON, thickness=bench.THICKNESS)
+    assert pst == 0
+    pre = dict(K=K.values_csr(), F=d_F.to_host(), PK=P.vals.copy(), PF=F.copy())
+    neu_dof, neu_add, dir_dof, dir_val = flatten_bcs(m, bench.workload_bcs())
+    api.vector_add_entries(d_F, neu_dof, neu_add)
+    K.apply_dirichlet(d_F, dir_dof, dir_val)
+    port.set_bconditions(m, P, F, bench.workload_bcs())
+    return dict(m=m, rs=rs, cols=cols, prs=prs, pcols=pcols, K=K, d_F=d_F, P=P, F=F, pre=pre, mesh=mesh)
+
+
+def test_pattern_counts_and_bits(q1):
+    N, nnz = meshgen.quad_counts(bench.NX, bench.NY_PER_GPU)           # SURVEY.md §8 closed form
+    assert (N, nnz) == (1003002, 18018004) == (q1["K"].N, q1["K"].nnz)
+    assert np.array_equal(q1["rs"], q1["prs"]) and np.array_equal(q1["cols"], q1["pcols"])
+    assert q1["K"].blocked and q1["K"].idx16 and q1["K"].sigma == 1
+    assert q1["K"].stored <= 1.003 * nnz
+
+
+def test_assembly_and_boundary_conditions_bit_exact(q1):
+    assert np.array_equal(q1["pre"]["K"], q1["pre"]["PK"]) and np.array_equal(q1["pre"]["F"], q1["pre"]["PF"])
+    assert np.array_equal(q1["K"].values_csr(), q1["P"].vals)
+    assert np.array_equal(q1["d_F"].to_host(), q1["F"])
+
+
+def test_spmv_bits_linearity_symmetry(q1):
+    K, P = q1["K"], q1["P"]
+    x = meshgen.uniform_rhs(K.N, seed=1)
+    y = meshgen.uniform_rhs(K.N, seed=2)
+    Kx, Ky = K.spmv_host(x), K.spmv_host(y)
+    assert np.array_equal(Kx, P.spmv(x, threads=os.cpu_count() or 1))    # same rounding, 1 M rows
+    assert rel_l2(K.spmv_host(x + 3.0 * y), Kx + 3.0 * Ky) <= 1e-15      # linearity
+    assert abs(np.dot(y, Kx) - np.dot(x, Ky)) <= 1e-12 * abs(np.dot(y, Kx))   # K symmetric after Dirichlet
+
+
+def test_first_iterations_bit_identical_in_reference_order(q1, nbgpu_lib):
+    """50 iterations at full size with the dots summed in the reference's order: same bits as the port."""
+    capi.check(nbgpu_lib.nbgpu_set_reduction_order(1))
+    try:
+        st, x, it, res = q1["K"].pcg_jacobi_host(q1["F"], tol=0.0, max_iter=50)
+    finally:
+        capi.check(nbgpu_lib.nbgpu_set_reduction_order(0))
+    ost, ox, oit, ores = q1["P"].pcg_jacobi(q1["F"], tol=0.0, max_iter=50, threads=1)
+    assert (st, it) == (ost, oit) == (1, 50)
+    assert np.array_equal(x, ox) and res == ores
+
+
+def test_full_solve_properties(q1):
+    """The headline solve (bench.py's step): converges, true residual at the asked tolerance, iteration count
+    within 2 % of the port's (16 host threads, ~10 s), same compliance."""
+    K, P, F = q1["K"], q1["P"], q1["F"]
+    tol = bench.REL_TOL * float(np.linalg.norm(F))
+    st, x, it, res = K.pcg_jacobi_host(F, tol=tol)
+    assert st == 0 and res <= tol
+    true_res = float(np.linalg.norm(K.spmv_host(x) - F))
+    assert true_res <= 1.5 * tol
+    ost, ox, oit, ores = P.pcg_jacobi(F, tol=tol, threads=os.cpu_count() or 1)
+    assert ost == 0 and abs(it - oit) <= 0.02 * oit, (it, oit)
+    assert abs(np.dot(F, x) - np.dot(F, ox)) <= 1e-9 * abs(np.dot(F, ox))     # compliance
+    assert rel_l2(x, ox) <= 1e-6          # both stopped at a 1e-8 residual; cond(K) ~ 1e7 bounds the gap
+    # deterministic: a second solve gives the same bits
+    st2, x2, it2, res2 = K.pcg_jacobi_host(F, tol=tol)
+    assert it2 == it and np.array_equal(x2, x)
+
+
+def test_laplacian_4m_rows(nbgpu_lib):
+    """configs[2] family at 2048^2 (4.2 M rows): SpMV bits against the port, symmetry, 16-bit ids in use."""
+    rs, cols, vals = meshgen.laplacian9_csr(2048)
+    A = api.Matrix.from_csr(rs, cols, vals)
+    assert A.idx16 and not A.blocked and A.max_width == 9
+    x = meshgen.uniform_rhs(A.N)
+    y = A.spmv_host(x)
+    assert np.array_equal(y, port.Csr(rs, cols, vals).spmv(x, threads=os.cpu_count() or 1))
+    z = meshgen.uniform_rhs(A.N, seed=5)
+    assert abs(np.dot(z, y) - np.dot(x, A.spmv_host(z))) <= 1e-12 * abs(np.dot(z, y))
+    st, sol, it, res = A.pcg_jacobi_host(x, tol=1e-8 * float(np.linalg.norm(x)))
+    assert st == 0 and float(np.linalg.norm(A.spmv_host(sol) - x)) <= 1.5e-8 * float(np.linalg.norm(x))
