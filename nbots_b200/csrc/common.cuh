@@ -14,7 +14,15 @@ namespace nbgpu {
 
 constexpr uint32_t kSliceRows = 32;           // SELL slice height = one warp
 constexpr uint32_t kPadCol = 0xFFFFFFFFu;     // column id of a padding entry
-constexpr int kBlock = 256;                   // threads per CTA of every streaming kernel
+// Threads per CTA of every streaming kernel.  320 = 10 warps: the streamed SpMV is bound by the per-warp
+// chain "ids -> gathers -> ordered accumulation", so warps per SM are what counts; two CTAs of 10 warps
+// (94 registers, two 4.9 KB stages per warp = 196 KB of shared memory) are the most that fit an SM.
+// Measured against 256 (8 warps, with the early stage release that 122 registers then allow):
+// Q1 47.0 -> 46.0 us/iteration, L4096 544 -> 515, ragged 1 M-dof mesh 47.7 -> 46.1, Q4 158.8 -> 161.5.
+#ifndef NB_BLOCK
+#define NB_BLOCK 320
+#endif
+constexpr int kBlock = NB_BLOCK;
 constexpr int kMaxPartialBlocks = 4096;       // upper bound on persistent grid sizes
 
 struct Context {

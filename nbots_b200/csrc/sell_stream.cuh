@@ -270,7 +270,12 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			}
 			return reinterpret_cast<const uint32_t *>(sids)[k * kStride + mine];
 		};
-		const bool single = (BLOCKED ? (width >> 1) : width) <= (uint32_t)kGatherBatch;
+#ifndef NB_EARLY
+#define NB_EARLY 2
+#endif
+		// NB_EARLY: 1 = both layouts, 2 = per-entry layout only (the blocked variant needs 122 registers)
+		const bool single = (NB_EARLY == 1 || (NB_EARLY == 2 && !BLOCKED)) &&
+				    (BLOCKED ? (width >> 1) : width) <= (uint32_t)kGatherBatch;
 		if (!BLOCKED && single) {
 			uint32_t cj[kGatherBatch];
 			double xj[kGatherBatch], vj[kGatherBatch];
