@@ -78,6 +78,7 @@ struct PeerTable {
 	uint32_t n_recv_src;               // ranks I receive a halo from
 	int recv_src[kMaxRanks];
 	unsigned long long timeout_ns;
+	int push_first;                    // A/B: halo push by warp 0 of every CTA (the first scheme)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -194,13 +195,13 @@ __device__ __forceinline__ bool cta_reduce_msgs(int world, SlotOf slot_of, unsig
 // destination's ack of the previous push first, the input halo is single-buffered).
 __device__ __forceinline__ void push_halo_piece(const PeerTable &T, const uint32_t *__restrict__ send_idx,
 						const double *v, int which, unsigned long long seq,
-						unsigned int *ticket)
+						unsigned int *ticket, uint32_t piece, uint32_t n_pieces)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t total = T.send_ptr[T.world];
 	DistControl *mine = T.ctrl[T.rank];
-	const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
-	const uint32_t b = min(total, blockIdx.x * per), e = min(total, b + per);
+	const uint32_t per = (total + n_pieces - 1) / n_pieces;
+	const uint32_t b = min(total, piece * per), e = min(total, b + per);
 	bool ok = true;
 	if (which == 1 && e > b) {
 		// destinations touched by [b, e)
@@ -225,8 +226,8 @@ __device__ __forceinline__ void push_halo_piece(const PeerTable &T, const uint32
 	}
 	__syncwarp();
 	if (lane == 0) {
-		const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-		if (t == gridDim.x - 1) {
+		const unsigned int t = atomicInc(ticket, n_pieces - 1);
+		if (t == n_pieces - 1) {
 			__threadfence_system();
 			for (int d = 0; d < T.world; d++)
 				if (T.send_ptr[d + 1] > T.send_ptr[d])
@@ -243,7 +244,7 @@ halo_push_kernel(PeerTable T, const uint32_t *__restrict__ send_idx, const doubl
 	pdl_launch_dependents();
 	if (*(volatile int *)&T.ctrl[T.rank]->error)
 		return;
-	push_halo_piece(T, send_idx, v, which, seq, ticket);
+	push_halo_piece(T, send_idx, v, which, seq, ticket, blockIdx.x, gridDim.x);
 }
 
 // post NV partial values into slot `rank` of every peer (called by one CTA, after its reduction)
@@ -367,11 +368,25 @@ dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned
 		A, p_ext, cfg, smem,
 		[&] {
 			active = iteration_gate(k, st) && !*(volatile int *)&T.ctrl[T.rank]->error;
-			// the boundary entries of p_k leave at the START of the kernel that consumes p_k
-			// (warp 0 of every CTA sends a piece while the other warps already stream the matrix);
-			// the neighbours only need them for their last slices (late wait below)
-			if (active && (threadIdx.x >> 5) == 0 && T.send_ptr[T.world] > 0)
-				push_halo_piece(T, send_idx, p_ext, 0, base + k + 1, &st->push_ticket);
+			// The boundary entries of p_k leave at the START of the kernel that consumes p_k, while the
+			// other warps already stream the matrix; the neighbours only need them for their last slices
+			// (late wait below).  A push costs its warp a system-scope fence (an NVLink round trip), so it
+			// is given to the LAST warp of the LAST CTAs, 32 values each: with slices dealt round-robin
+			// those warps own one slice fewer than the first ones whenever the division leaves a rest.
+			const uint32_t total = T.send_ptr[T.world];
+			if (active && total > 0) {
+				if (T.push_first) {
+					if ((threadIdx.x >> 5) == 0)
+						push_halo_piece(T, send_idx, p_ext, 0, base + k + 1, &st->push_ticket, blockIdx.x,
+								gridDim.x);
+				} else {
+					const uint32_t n_push = min(gridDim.x, (total + 31u) / 32u);
+					const uint32_t first_cta = gridDim.x - n_push;
+					if ((threadIdx.x >> 5) == kStreamWarps - 1 && blockIdx.x >= first_cta)
+						push_halo_piece(T, send_idx, p_ext, 0, base + k + 1, &st->push_ticket,
+								blockIdx.x - first_cta, n_push);
+				}
+			}
 			return active;
 		},
 		[&] { return warp_wait_halo(T, 0, base + k + 1); },   // only the slices that read halo columns wait
@@ -416,6 +431,12 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 	pdl_wait();
 	pdl_launch_dependents();
 	DistControl *mine = T.ctrl[T.rank];
+	// w of the first trip is fetched while the peers' p.w partials are still travelling
+	double wf0 = 0, wf1 = 0;
+	if (base_i < N) {
+		wf0 = w[base_i];
+		wf1 = w[base_i + stride < N ? base_i + stride : base_i];
+	}
 	double pw_tot[1];
 	if (!cta_reduce_msgs<1>(T.world, [&](int r, int) { return &mine->pw_msg[r]; }, base + k + 1, mine, T.timeout_ns,
 				&st->done, pw_tot))
@@ -437,7 +458,7 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 				d1 = diag[j1];
 			}
 		}
-		const double w0 = w[i0], w1 = w[j1];
+		const double w0 = i0 == base_i ? wf0 : w[i0], w1 = i0 == base_i ? wf1 : w[j1];
 		const double gn0 = __dadd_rn(g0, __dmul_rn(alpha, w0));
 		const double gn1 = __dadd_rn(g1, __dmul_rn(alpha, w1));
 		g[i0] = gn0;
@@ -462,10 +483,12 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		post_gq(T, tot[0], JACOBI ? tot[1] : tot[0], base + k + 2);
 }
 
-// ---- K3: waits for all (g.g, g.q), x += alpha p, p = -q + beta p --------------------
+// ---- K3: x += alpha p, waits for all (g.g, g.q), p = -q + beta p --------------------
+// The x update needs only alpha (known since K2), so it runs BEFORE the wait: the partials of the peers
+// travel while it executes.  p is read a second time afterwards (an L2 hit).
 __global__ void __launch_bounds__(kBlock)
 dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, const double *__restrict__ q,
-		double *__restrict__ p, double *__restrict__ x, DistState *st)
+		double *__restrict__ p, double *__restrict__ x, DistState *st, int x_first)
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const uint32_t base_i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -480,18 +503,10 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 	pdl_wait();
 	pdl_launch_dependents();
 	DistControl *mine = T.ctrl[T.rank];
-	double tot[2];
-	if (!cta_reduce_msgs<2>(T.world, [&](int r, int c) { return &mine->gq_msg[r][c]; }, base + k + 2, mine,
-				T.timeout_ns, &st->done, tot))
-		return;
-	const double gg = tot[0], gq = tot[1];
-	const double beta = __ddiv_rn(gq, st->gq[k & 1]);
+	if (*(volatile const int32_t *)&st->done || *(volatile int *)&mine->error)
+		return;   // grid-uniform: set by the gate of K1(k) / by a failed wait earlier in the stream
 	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);   // the update kernel stored pw
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		st->gg[(k + 1) % 3u] = gg;
-		st->gq[(k + 1) & 1] = gq;
-	}
-	for (uint32_t i0 = base_i; i0 < N; i0 += 2 * stride) {
+	for (uint32_t i0 = base_i; x_first && i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
@@ -501,13 +516,34 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 			x0 = x[i0];
 			x1 = x[j1];
 		}
-		const double q0 = q[i0], q1 = q[j1];
 		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
-		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, p0));
-		if (has1) {
+		if (has1)
 			x[i1] = __dadd_rn(x1, __dmul_rn(alpha, p1));
-			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
+	}
+	double tot[2];
+	if (!cta_reduce_msgs<2>(T.world, [&](int r, int c) { return &mine->gq_msg[r][c]; }, base + k + 2, mine,
+				T.timeout_ns, &st->done, tot))
+		return;
+	const double gg = tot[0], gq = tot[1];
+	const double beta = __ddiv_rn(gq, st->gq[k & 1]);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		st->gg[(k + 1) % 3u] = gg;
+		st->gq[(k + 1) & 1] = gq;
+	}
+	for (uint32_t i0 = base_i; i0 < N; i0 += 2 * stride) {
+		const uint32_t i1 = i0 + stride;
+		const bool has1 = i1 < N;
+		const uint32_t j1 = has1 ? i1 : i0;
+		const double q0 = q[i0], q1 = q[j1];
+		const double pa = p[i0], pb = p[j1];
+		if (!x_first) {
+			x[i0] = __dadd_rn(x[i0], __dmul_rn(alpha, pa));
+			if (has1)
+				x[i1] = __dadd_rn(x[i1], __dmul_rn(alpha, pb));
 		}
+		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, pa));
+		if (has1)
+			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, pb));
 	}
 }
 
@@ -932,6 +968,8 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 	const int dgrid = resident_grid(dist_dir_kernel, vec_blocks);
 	const int n_dst = n_destinations(P);
 	const bool pdl = !getenv("NBGPU_NO_PDL");
+	const int x_first = getenv("NBGPU_DIST_X_LATE") ? 0 : 1;   // A/B switch of the direction kernel
+	T.push_first = getenv("NBGPU_DIST_PUSH_FIRST") ? 1 : 0;
 	// the x-halo exchange shares its flags with nbgpu_dist_spmv: one counter for both
 	const unsigned long long xseq = ++D->spmv_seq;
 	const unsigned long long base = D->seq_base;
@@ -978,7 +1016,7 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 				e = launch(pdl, dist_update_kernel<false>, ugrid, kBlock, 0, k, N, T, base, (const double *)w,
 					   (const double *)diag, g, q, c.partials, st);
 			NB_CUDA(e);
-			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p, xw, st));
+			NB_CUDA(launch(pdl, dist_dir_kernel, dgrid, kBlock, 0, k, N, T, base, (const double *)q, p, xw, st, x_first));
 		}
 		if (k == max_iter) {
 			if (A->blocked)
