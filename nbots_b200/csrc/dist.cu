@@ -483,9 +483,9 @@ dist_update_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base,
 		post_gq(T, tot[0], JACOBI ? tot[1] : tot[0], base + k + 2);
 }
 
-// ---- K3: x += alpha p, waits for all (g.g, g.q), p = -q + beta p --------------------
-// The x update needs only alpha (known since K2), so it runs BEFORE the wait: the partials of the peers
-// travel while it executes.  p is read a second time afterwards (an L2 hit).
+// ---- K3: waits for all (g.g, g.q), x += alpha p, p = -q + beta p --------------------
+// x_first: the x update needs only alpha (known since K2) and can run BEFORE the wait, while the partials
+// of the peers travel; p is then read a second time.  Measured neutral (2 GPUs) to slower (1 GPU): off.
 __global__ void __launch_bounds__(kBlock)
 dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, const double *__restrict__ q,
 		double *__restrict__ p, double *__restrict__ x, DistState *st, int x_first)
@@ -968,7 +968,9 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 	const int dgrid = resident_grid(dist_dir_kernel, vec_blocks);
 	const int n_dst = n_destinations(P);
 	const bool pdl = !getenv("NBGPU_NO_PDL");
-	const int x_first = getenv("NBGPU_DIST_X_LATE") ? 0 : 1;   // A/B switch of the direction kernel
+	// x += alpha p before the wait for the peers' partials (p is then read twice) measured neutral on
+	// 2 GPUs and 0.9 us slower on 1; off unless asked for
+	const int x_first = getenv("NBGPU_DIST_X_FIRST") ? 1 : 0;
 	T.push_first = getenv("NBGPU_DIST_PUSH_FIRST") ? 1 : 0;
 	// the x-halo exchange shares its flags with nbgpu_dist_spmv: one counter for both
 	const unsigned long long xseq = ++D->spmv_seq;
