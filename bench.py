@@ -206,7 +206,7 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get("krylov_spmv_kernel_dram_bytes_per_launch")
     ach = bytes_spmv / (per[0] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "krylov_spmv_stream_kernel<blocked> (SpMV + p.w, TMA-staged SELL-32)", "achieved": round(ach, 1),
+    roofline = {"bound": "hbm", "kernel": "krylov_spmv_stream_kernel<blocked, 16-bit ids> (SpMV + p.w, TMA-staged SELL-32)", "achieved": round(ach, 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": traffic, "algorithmic_bytes_per_launch": bytes_spmv,
                 "ms_per_launch": round(float(per[0]), 5), "launches_timed": int(n_prof.value),
