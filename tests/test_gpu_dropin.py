@@ -130,3 +130,14 @@ def test_shim_entry_points_tolerate_concurrent_callers(nbgpu_lib):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("env", [{"NBGPU_NO_POOL": "1"}, {"NBGPU_SPMV_PATH": "reg"}, {"NBGPU_NO_PDL": "1"}])
+def test_fallback_configurations_still_pass_smoke(nbgpu_lib, env):
+    """Process-wide switches (plain cudaMalloc instead of the pool, register-path SpMV, no programmatic
+    dependent launch) are read once per process: run the smoke check under each in a fresh interpreter."""
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=e,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "smoke ok" in out.stdout, out.stdout + out.stderr
