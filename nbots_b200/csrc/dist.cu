@@ -295,7 +295,7 @@ __device__ __forceinline__ bool warp_wait_halo(const PeerTable &T, int which, un
 
 // ---- init: g = A x - b, q = g / diag, p = -q; posts the partial (g.g, g.q) ------
 template <bool JACOBI, bool BLOCKED>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kStreamCtas)
 dist_init_kernel(SellView A, StreamConfig cfg, PeerTable T, unsigned long long seq, unsigned long long gseq,
 		 const double *__restrict__ b,
 		 const double *__restrict__ x_ext, double *__restrict__ g, double *__restrict__ p,
@@ -356,7 +356,7 @@ __global__ void dist_init_reduce_kernel(PeerTable T, unsigned long long seq, Dis
 
 // ---- K1: halo wait, gate, w = A p, posts the partial p.w ---------------------------
 template <bool BLOCKED>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kStreamCtas)
 dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned long long base,
 		 const uint32_t *__restrict__ send_idx, const double *__restrict__ p_ext, double *__restrict__ w,
 		 double *partials, DistState *st)
@@ -549,7 +549,7 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 
 // ---- distributed SpMV (config 3): y = A x with the halo of x exchanged first --------
 template <bool BLOCKED>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kStreamCtas)
 dist_plain_spmv_kernel(SellView A, StreamConfig cfg, PeerTable T, unsigned long long seq,
 		       const double *__restrict__ x_ext, double *__restrict__ y, unsigned int *ticket)
 {

@@ -185,7 +185,7 @@ krylov_spmv_kernel(uint32_t k, uint32_t N, uint32_t n_slices, const uint32_t *__
 
 // ---- streamed path: the matrix goes through shared memory (sell_stream.cuh) -----
 template <bool JACOBI, int LAYOUT>   // LAYOUT = blocked | idx16 << 1
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kStreamCtas)
 krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ b,
 			  const double *__restrict__ x, double *__restrict__ g, double *__restrict__ p,
 			  double *__restrict__ q, double *__restrict__ diag, double *partials, KrylovState *st)
@@ -202,7 +202,7 @@ krylov_init_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kStreamCtas)
 krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, const double *__restrict__ p,
 			  double *__restrict__ w, double *partials, KrylovState *st)
 {

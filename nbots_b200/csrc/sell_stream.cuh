@@ -88,6 +88,10 @@ __device__ __forceinline__ double2 ld_gather_f64x2(const double *p)
 
 // ------------------------------------------------------------- geometry ----
 constexpr int kStreamWarps = kBlock / 32;      // consumer warps per CTA
+#ifndef NB_STREAM_CTAS
+#define NB_STREAM_CTAS 2
+#endif
+constexpr int kStreamCtas = NB_STREAM_CTAS;    // CTAs per SM the streamed kernels are compiled for
 constexpr int kStreamMaxStages = 6;
 constexpr int kGatherBatch = 9;                // gathers in flight per lane
 

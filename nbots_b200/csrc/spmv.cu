@@ -28,7 +28,7 @@ spmv_sell_kernel(uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ sli
 }
 
 template <int LAYOUT>   // blocked | idx16 << 1
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kStreamCtas)
 spmv_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ x, double *__restrict__ y)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -54,7 +54,7 @@ bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cf
 	const uint32_t fixed = kStreamWarps * kStreamMaxStages * (sizeof(uint64_t) + sizeof(uint2));
 	int smem_optin = 0;
 	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx().device);
-	int want_ctas = getenv("NBGPU_STREAM_CTAS") ? atoi(getenv("NBGPU_STREAM_CTAS")) : 2;
+	int want_ctas = getenv("NBGPU_STREAM_CTAS") ? atoi(getenv("NBGPU_STREAM_CTAS")) : kStreamCtas;
 	int want_stages = getenv("NBGPU_STREAM_STAGES") ? atoi(getenv("NBGPU_STREAM_STAGES")) : 0;
 	for (int ctas = want_ctas; ctas >= 1; ctas--) {
 		// 228 KB per SM, 1 KB reserved per CTA, some static shared memory for the reductions
