@@ -535,11 +535,15 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 		const bool has1 = i1 < N;
 		const uint32_t j1 = has1 ? i1 : i0;
 		const double q0 = q[i0], q1 = q[j1];
-		const double pa = p[i0], pb = p[j1];
+		// the first trip's p and x were fetched before the dependency wait (the x_first pass reuses
+		// those registers for its later trips, so it reloads)
+		const bool pre = !x_first && i0 == base_i;
+		const double pa = pre ? p0 : p[i0], pb = pre ? p1 : p[j1];
 		if (!x_first) {
-			x[i0] = __dadd_rn(x[i0], __dmul_rn(alpha, pa));
+			const double xa = pre ? x0 : x[i0], xb = pre ? x1 : x[j1];
+			x[i0] = __dadd_rn(xa, __dmul_rn(alpha, pa));
 			if (has1)
-				x[i1] = __dadd_rn(x[i1], __dmul_rn(alpha, pb));
+				x[i1] = __dadd_rn(xb, __dmul_rn(alpha, pb));
 		}
 		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, pa));
 		if (has1)
