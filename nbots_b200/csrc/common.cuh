@@ -51,6 +51,10 @@ void set_error(const char *fmt, ...);
 int ensure_stage(size_t bytes);
 int ensure_workspace(size_t bytes);
 
+// host <-> device vectors through the pinned staging buffers (matrix.cu); both block until done
+int upload_vector(double *d_dst, const double *src, size_t n);
+int download_vector(double *dst, const double *d_src, size_t n);
+
 // L2 residency control for a solve (context.cu)
 bool l2_pin(void *ptr, size_t bytes, bool others_streaming);
 void l2_unpin();

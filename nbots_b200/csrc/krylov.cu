@@ -617,28 +617,21 @@ int solve_host(const nbgpu_matrix_t *A, const double *b, double *x, uint32_t max
 {
 	NB_INIT();
 	NB_ARG(A != nullptr && b != nullptr && x != nullptr);
-	Context &c = ctx();
-	const size_t bytes = (size_t)A->N * sizeof(double);
 	const size_t Np = ((size_t)A->N + 1) & ~(size_t)1;
 	double *d_b = nullptr, *d_x = nullptr;
 	NB_TRY(nbgpu_malloc((void **)&d_b, 2 * Np * sizeof(double)));
 	d_x = d_b + Np;
-	int st = NBGPU_OK;
-	if (cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, c.stream) != cudaSuccess ||
-	    cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, c.stream) != cudaSuccess) {
-		set_error("upload of b/x failed: %s", cudaGetErrorString(cudaGetLastError()));
-		st = NBGPU_ERR_CUDA;
-	}
+	int st = upload_vector(d_b, b, A->N);
+	if (st == NBGPU_OK)
+		st = upload_vector(d_x, x, A->N);
 	int solver_status = NBGPU_OK;
 	if (st == NBGPU_OK) {
 		solver_status = solve(A, d_b, d_x, max_iter, tol, niter, tol_reached, jacobi);
 		if (solver_status != NBGPU_OK && solver_status != NBGPU_NOT_CONVERGED)
 			st = solver_status;
 	}
-	if (st == NBGPU_OK && cudaMemcpy(x, d_x, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
-		set_error("download of x failed: %s", cudaGetErrorString(cudaGetLastError()));
-		st = NBGPU_ERR_CUDA;
-	}
+	if (st == NBGPU_OK)
+		st = download_vector(x, d_x, A->N);
 	nbgpu_free(d_b);
 	return st != NBGPU_OK ? st : solver_status;
 }
