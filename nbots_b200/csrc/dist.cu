@@ -266,10 +266,16 @@ __device__ __forceinline__ uint32_t gate_slot(uint32_t k) { return k == 0 ? 0u :
 
 __device__ __forceinline__ bool iteration_gate(uint32_t k, DistState *st)
 {
-	if (*(volatile int32_t *)&st->done)
+	// plain loads issued together: see iteration_gate in krylov.cu (the state line is read by every
+	// warp of the grid; volatile loads make it an L2 hot spot)
+	const DistState *cs = st;
+	const int32_t done = cs->done;
+	const double gg = cs->gg[gate_slot(k)];
+	const double tol2 = cs->tol2;
+	const uint32_t max_iter = cs->max_iter;
+	if (done)
 		return false;
-	const double gg = st->gg[gate_slot(k)];
-	if (gg > st->tol2 && k < st->max_iter)
+	if (gg > tol2 && k < max_iter)
 		return true;
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		st->k_final = k;
@@ -367,7 +373,8 @@ dist_spmv_kernel(uint32_t k, SellView A, StreamConfig cfg, PeerTable T, unsigned
 	sell_stream_rows<BLOCKED, false, false>(
 		A, p_ext, cfg, smem,
 		[&] {
-			active = iteration_gate(k, st) && !*(volatile int *)&T.ctrl[T.rank]->error;
+			const int failed = T.ctrl[T.rank]->error;   // plain: a stale 0 only delays the exit
+			active = iteration_gate(k, st) && !failed;
 			// The boundary entries of p_k leave at the START of the kernel that consumes p_k, while the
 			// other warps already stream the matrix; the neighbours only need them for their last slices
 			// (late wait below).  A push costs its warp a system-scope fence (an NVLink round trip), so it
@@ -503,7 +510,9 @@ dist_dir_kernel(uint32_t k, uint32_t N, PeerTable T, unsigned long long base, co
 	pdl_wait();
 	pdl_launch_dependents();
 	DistControl *mine = T.ctrl[T.rank];
-	if (*(volatile const int32_t *)&st->done || *(volatile int *)&mine->error)
+	const int32_t done = st->done;    // plain loads: every thread of the grid reads these two words
+	const int failed = mine->error;
+	if (done || failed)
 		return;   // grid-uniform: set by the gate of K1(k) / by a failed wait earlier in the stream
 	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);   // the update kernel stored pw
 	for (uint32_t i0 = base_i; x_first && i0 < N; i0 += 2 * stride) {

@@ -74,10 +74,20 @@ __device__ __forceinline__ uint32_t gate_slot(uint32_t k) { return k == 0 ? 0u :
 // otherwise records the exit (once) and makes every later kernel a no-op.
 __device__ __forceinline__ bool iteration_gate(uint32_t k, KrylovState *st)
 {
-	if (*(volatile int32_t *)&st->done)
+	// All four loads are issued before the first use (one round trip at the head of the kernel instead
+	// of two; ncu: 17 % of the SpMV kernel's stall samples sat on this chain), as PLAIN loads: a warp
+	// coalesces them and the first warp of a CTA leaves the line in L1 for the others.  Every thread of
+	// the grid reads the same 64 bytes, so `volatile` or L2-only (`ld.cg`) loads turn that line into a
+	// hot spot (measured: K2/K3 +3 to +6 us).  The values were written by an earlier kernel of the
+	// stream, or, for `done`, lead every CTA of this kernel to the same decision.
+	const KrylovState *cs = st;
+	const int32_t done = cs->done;
+	const double gg = cs->gg[gate_slot(k)];
+	const double tol2 = cs->tol2;
+	const uint32_t max_iter = cs->max_iter;
+	if (done)
 		return false;
-	const double gg = st->gg[gate_slot(k)];
-	if (gg > st->tol2 && k < st->max_iter)
+	if (gg > tol2 && k < max_iter)
 		return true;
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		st->k_final = k;
@@ -251,9 +261,11 @@ krylov_update_kernel(uint32_t k, uint32_t N, const double *__restrict__ w, const
 	}
 	pdl_wait();
 	pdl_launch_dependents();
-	if (*(volatile int32_t *)&st->done)
+	const int32_t done = st->done;   // plain loads of the shared state line, see iteration_gate
+	const double gq_k = st->gq[k & 1], pw_k = st->pw;
+	if (done)
 		return;
-	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);
+	const double alpha = __ddiv_rn(gq_k, pw_k);
 	double dots[2] = {0.0, 0.0};
 	for (uint32_t i0 = base; i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
@@ -315,10 +327,13 @@ krylov_dir_kernel(uint32_t k, uint32_t N, const double *__restrict__ q, double *
 	}
 	pdl_wait();
 	pdl_launch_dependents();
-	if (*(volatile const int32_t *)&st->done)
+	const int32_t done = st->done;   // plain loads of the shared state line, see iteration_gate
+	const double gq_k = st->gq[k & 1], gq_n = st->gq[(k + 1) & 1];
+	const double pw_k = st->pw;
+	if (done)
 		return;
-	const double alpha = __ddiv_rn(st->gq[k & 1], st->pw);
-	const double beta = __ddiv_rn(st->gq[(k + 1) & 1], st->gq[k & 1]);
+	const double alpha = __ddiv_rn(gq_k, pw_k);
+	const double beta = __ddiv_rn(gq_n, gq_k);
 	for (uint32_t i0 = base; i0 < N; i0 += 2 * stride) {
 		const uint32_t i1 = i0 + stride;
 		const bool has1 = i1 < N;
