@@ -22,6 +22,18 @@
 // NODE id per 2x2 block (a quarter of the ids: 9 instead of 12 bytes per entry)
 // and the gather fetches x[2c], x[2c+1] as one 16-byte load.  The accumulation
 // order per row is unchanged.
+//
+// IDX16: for banded numberings the ids are stored as int16 differences to the
+// row's own index (node index when BLOCKED), padding = -32768: 10 / 8.5 bytes
+// per entry instead of 12 / 9.
+//
+// What bounds the kernel (ncu source page, Q1): the per-warp chain
+// "ids from shared memory -> gathers of x -> ordered accumulation"; a third of
+// all stall samples sit on the first use of a gathered value.  Hence 10 warps
+// per CTA rather than 8 with more registers, and no early stage release in the
+// blocked variant (NB_EARLY, see the loop).  Not bytes in flight, not L1/LSU
+// capacity to spare either: a `prefetch.global.L1` of the next slice's gather
+// targets made the kernel 17 % slower (28 KB of L1 left beside the stages).
 #pragma once
 
 #include "spmv.cuh"
