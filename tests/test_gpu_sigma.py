@@ -154,3 +154,47 @@ def test_far_columns_keep_32_bit_ids(nbgpu_lib, monkeypatch):
     rs3 = np.array([r.size for r in rows], dtype=np.uint32)
     c3 = np.concatenate(rows).astype(np.uint32)
     assert not api.Matrix.from_csr(rs3, c3).idx16
+
+
+@pytest.mark.parametrize("ids", ["16", "32"])
+@pytest.mark.parametrize("window", ["1", "128"])
+def test_streamed_path_with_several_gather_batches(nbgpu_lib, monkeypatch, ids, window):
+    """Per-entry layout with slices 10..24 entries wide: the streamed kernel then takes its general loop
+    (full gather batches + tail) instead of the single-batch path of the 9-point stencil, with both id
+    widths and with sorted rows."""
+    monkeypatch.setenv("NBGPU_SIGMA", window)
+    monkeypatch.setenv("NBGPU_SPMV_PATH", "stream")
+    if ids == "32":
+        monkeypatch.setenv("NBGPU_NO_IDX16", "1")
+    rng = np.random.default_rng(17)
+    N = 5003
+    rs = rng.integers(0, 25, N).astype(np.uint32)
+    rs[:40] = 24                                            # a few slices of full width right away
+    rows = [np.unique(np.clip(i + rng.integers(-300, 301, k), 0, N - 1)) for i, k in enumerate(rs)]
+    rs = np.array([r.size for r in rows], dtype=np.uint32)
+    cols = np.concatenate(rows).astype(np.uint32)
+    vals = rng.standard_normal(cols.size)
+    A = api.Matrix.from_csr(rs, cols, vals)
+    assert not A.blocked and A.idx16 == (ids == "16") and 9 < A.max_width <= 24
+    P = port.Csr(rs, cols, vals)
+    for seed in (1, 2):
+        x = rng.standard_normal(N)
+        assert np.array_equal(A.spmv_host(x), P.spmv(x))
+    # a diagonally dominant symmetric matrix of the same shape class, solved by both
+    n = 3001
+    off = [[j for j in (i + rng.integers(-60, 61, 5)).tolist() if 0 <= j < n] for i in range(n)]
+    pairs = {(min(i, j), max(i, j)) for i, c in enumerate(off) for j in c if i != j}
+    adj = [[] for _ in range(n)]
+    for i, j in pairs:
+        adj[i].append(j); adj[j].append(i)
+    rows = [np.array(sorted(a + [i])) for i, a in enumerate(adj)]
+    rs2 = np.array([r.size for r in rows], dtype=np.uint32)
+    c2 = np.concatenate(rows).astype(np.uint32)
+    v2 = np.concatenate([np.where(r == i, float(r.size) + 1.0, -1.0) for i, r in enumerate(rows)])
+    B = api.Matrix.from_csr(rs2, c2, v2)
+    assert 9 < B.max_width <= 28 and not B.blocked
+    b = rng.standard_normal(n)
+    st, x, it, res = B.pcg_jacobi_host(b, tol=1e-10 * float(np.linalg.norm(b)))
+    ost, ox, oit, ores = port.Csr(rs2, c2, v2).pcg_jacobi(b, tol=1e-10 * float(np.linalg.norm(b)))
+    assert st == ost == 0 and abs(it - oit) <= max(1, int(0.02 * oit))
+    assert np.linalg.norm(x - ox) <= 1e-10 * np.linalg.norm(ox)
