@@ -65,6 +65,52 @@ def test_pattern_builder_scalar_and_ragged():
     assert np.array_equal(rs, prs) and np.array_equal(cols, pcols) and rs[-1] == 2
 
 
+def test_pattern_builder_list_cache_is_validated():
+    """The sizing call keeps its sorted node lists for the fill call; a mesh that changes in place between
+    the two calls (same buffers, same sizes) must not be served from that cache, and high-degree nodes take
+    the general sort."""
+    import ctypes as C
+    L = capi.lib()
+    a = meshgen.structured_mesh(40, 30, 2.0, 1.0, kind=0, diagonal_seed=1)
+    b = meshgen.structured_mesh(40, 30, 2.0, 1.0, kind=0, diagonal_seed=2)
+    adj = a.adj.copy()
+    rs = np.empty(a.n_nod * 2, dtype=np.uint32)
+    nnz = C.c_uint64(0)
+
+    def call(cols):
+        capi.check(L.nbgpu_pattern_from_mesh(a.n_nod, a.n_elems, 3, adj.ctypes.data_as(capi.u32p), 0, None, 2,
+                                             rs.ctypes.data_as(capi.u32p),
+                                             None if cols is None else cols.ctypes.data_as(capi.u32p), C.byref(nnz)))
+
+    call(None)                                             # sizing call on mesh a: lists cached
+    adj[:] = b.adj                                         # same buffer, other triangles
+    call(None)
+    cols = np.empty(nnz.value, dtype=np.uint32)
+    call(cols)
+    prs, pcols = port.pattern_from_mesh(b)                 # elements only would differ from edges+elements
+    brs, bcols = api.pattern_from_mesh(b, use_edges=False)
+    assert np.array_equal(rs, brs) and np.array_equal(cols, bcols)
+    assert np.array_equal(brs, prs) and np.array_equal(bcols, pcols)
+    # fill call with a changed mesh and NO new sizing call: rebuilt, not reused
+    adj[:] = a.adj
+    rs_a, cols_a = api.pattern_from_mesh(a, use_edges=False)
+    cols2 = np.empty(cols_a.size, dtype=np.uint32)
+    call(cols2)
+    assert np.array_equal(rs, rs_a) and np.array_equal(cols2, cols_a)
+    # a fan: node 0 belongs to 40 triangles (more neighbours than the small-list sort handles)
+    k = 40
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    nod = np.concatenate([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], axis=1).ravel()])
+    tri = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.uint32)
+    edges = np.array([[0, 1 + i] for i in range(k)] + [[1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.uint32)
+    fan = meshgen.Mesh2D(kind=0, nod=nod, edg=edges.ravel().copy(), adj=tri.ravel().copy(),
+                         vtx=np.zeros(0, np.uint32), sgm_sizes=np.zeros(0, np.uint32),
+                         sgm_nodes=np.zeros(0, np.uint32), nx=0, ny=0)
+    frs, fcols = api.pattern_from_mesh(fan)
+    prs, pcols = port.pattern_from_mesh(fan)
+    assert frs[0] == 2 * (k + 1) and np.array_equal(frs, prs) and np.array_equal(fcols, pcols)
+
+
 def test_tables_and_constitutive_match_reference():
     for npe, et in ((3, 0), (4, 1)):
         t = api.elem_tables(npe)
