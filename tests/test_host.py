@@ -149,3 +149,30 @@ def test_meshgen_counts():
     assert meshgen.quad_counts(4000, 2000) == (16012002, 288072004)    # Q16
     a = meshgen.uniform_rhs(100, seed=5)
     assert np.array_equal(a[10:30], meshgen.uniform_rhs(20, seed=5, start=10))
+
+
+def test_streamed_kernels_fit_two_ctas_per_sm():
+    """Static guard on the built library (no GPU needed): every TMA-streamed kernel must stay within the
+    register budget of two 320-thread CTAs per SM (65536 / 640 -> 96 after allocation rounding) without
+    spilling, and the bulk-copy / mbarrier instructions must be in its SASS."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    found = 0
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        name, reg, stack = m.group(1), int(m.group(2)), int(m.group(3))
+        if any(k in name for k in ("spmv_stream_kernel", "init_stream_kernel", "dist_spmv_kernel",
+                                    "dist_init_kernel", "dist_plain_spmv_kernel")):
+            found += 1
+            assert stack == 0, (name, "spills")
+            assert reg <= 96, (name, reg)
+    assert found >= 20          # 4 layouts x (spmv, krylov spmv, 2 x init) + the distributed kernels
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "nbgpu::spmv_stream_kernel<(int)3>", capi.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    if "UBLKCP" not in sass:    # older cuobjdump builds want the mangled name
+        sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass
