@@ -132,13 +132,20 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         dist.init_process_group("gloo")
         return rank, world, dist
+    if os.environ.get("NBGPU_BENCH_FORCE_DIST"):
+        # diagnostic: the row-partitioned code path with a world of one rank (its fixed overhead)
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+        return 0, 1, dist
     return rank, world, None
 
 
 def run_ours(args):
     from nbots_b200 import api, capi
     rank, world, dist = dist_setup(args.gpus)
-    if world > 1:
+    if dist is not None:
         from nbots_b200 import multigpu
         return multigpu.bench(args, rank, world, dist)
 

@@ -61,6 +61,10 @@ void *nbgpu_stream(void);
 int nbgpu_device_info(char *buf, size_t len);
 /* number of kernels this library has launched so far (for `gpu_launches`) */
 uint64_t nbgpu_launch_count(void);
+/* Give the CALLING host thread a context of its own on `device` (its stream, pool,
+ * workspace): the single-process multi-GPU mode runs one such thread per GPU.
+ * device < 0 returns the thread to the process-wide context. */
+int nbgpu_thread_bind_device(int device);
 
 int nbgpu_malloc(void **d_ptr, size_t bytes);
 int nbgpu_free(void *d_ptr);
@@ -116,6 +120,8 @@ int nbgpu_matrix_reset(nbgpu_matrix_t *A);
 /* nb_sparse_multiply_vector (sparse.c:405-414): out = A in.  Each row is
  * summed in ascending column order with separately rounded products and sums,
  * i.e. the same floating-point result as the reference loop. */
+/* d_in must be 16-byte aligned (nbgpu_malloc blocks are) when the matrix uses the
+ * 2x2-blocked layout; otherwise NBGPU_ERR_ARG. */
 int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out);
 int nbgpu_spmv_host(const nbgpu_matrix_t *A, const double *in, double *out);
 
@@ -150,6 +156,23 @@ int nbgpu_cg_host(const nbgpu_matrix_t *A, const double *b, double *x,
  *                bit-identical to the reference's: same iterates, same iteration
  *                count, same tolerance_reached.  Slow; for parity checks. */
 int nbgpu_set_reduction_order(int mode);
+
+/* Formulation of the iteration (parallel-tree mode only; reduction order 1 always
+ * runs the classic recurrence):
+ *   0 (default)  CLASSIC: the reference's recurrence (cg_precond_jacobi.c:45-76),
+ *                three kernels, two dependent reductions.
+ *   1            FUSED (opt-in): the matrix is applied to q, w = A p is carried by
+ *                recurrence and g.q, q.Aq, g.g are reduced together (Chronopoulos &
+ *                Gear): two kernels and ONE reduction per iteration -- one exchange
+ *                between GPUs instead of two.  Same iterates in exact arithmetic and
+ *                the same converged field (1e-10), identical iteration counts on the
+ *                cantilever workloads, but not the same rounding: on ill-conditioned
+ *                systems the count can leave the +-2 % band (void-material fixture:
+ *                359 vs 385).  Pays for systems whose work vectors stay in L2
+ *                (250 k dof: -15 % time) and for latency-bound multi-GPU runs; costs
+ *                +12 % vector traffic beyond that (4 M dof: +13 % time).
+ *  -1            back to the default / NBGPU_PCG_MODE=classic|fused. */
+int nbgpu_set_pcg_mode(int mode);
 
 /* Per-kernel timing of the solvers: when enabled, CUDA events bracket the three
  * kernels of each of the first 256 iterations of the next solves, on the
@@ -401,10 +424,17 @@ typedef struct nbgpu_dist_plan_s nbgpu_dist_plan_t;   /* halo / send lists of on
 
 #define NBGPU_IPC_HANDLE_BYTES 64
 
-/* a rank-local block of the matrix: N_rows owned rows, columns numbered
- * "owned, then halo" (see nbgpu_dist_plan_local_cols), entries of a row left in
- * ascending GLOBAL column order */
-int nbgpu_matrix_create_local(uint32_t N_rows, uint32_t N_cols,
+/* Column space of a rank-local block: "lower halo | owned | upper halo" -- the global
+ * order with the remote ranges squeezed out, each part starting on its own
+ * 128-byte line: lower halo at 0, owned columns at off_own, upper halo at off_up,
+ * ext_len entries in all. */
+int nbgpu_dist_ext_layout(uint32_t n_lo, uint32_t N_loc, uint32_t n_hi,
+			  uint32_t *off_own, uint32_t *off_up, uint32_t *ext_len);
+
+/* a rank-local block of the matrix: N_rows owned rows over a column space of
+ * N_cols (= ext_len) entries in which row r is column r + col_shift (= off_own);
+ * cols_local from nbgpu_dist_plan_local_cols (ascending, like the global ids) */
+int nbgpu_matrix_create_local(uint32_t N_rows, uint32_t N_cols, uint32_t col_shift,
 			      const uint32_t *rows_size,
 			      const uint32_t *cols_local, const double *vals,
 			      nbgpu_matrix_t **out);
@@ -419,22 +449,31 @@ int nbgpu_dist_plan_destroy(nbgpu_dist_plan_t *plan);
 /* recv_counts[world]: how many halo values come from each rank */
 int nbgpu_dist_plan_info(const nbgpu_dist_plan_t *plan, uint32_t *N_loc,
 			 uint32_t *n_halo, uint64_t *nnz, uint32_t *recv_counts);
+/* n_lo halo columns lie below the owned range; layout as nbgpu_dist_ext_layout */
+int nbgpu_dist_plan_layout(const nbgpu_dist_plan_t *plan, uint32_t *n_lo,
+			   uint32_t *off_own, uint32_t *off_up, uint32_t *ext_len);
 /* the halo columns (global row ids, ascending => grouped by owner) */
 int nbgpu_dist_plan_halo_ids(const nbgpu_dist_plan_t *plan, uint32_t *halo_global);
 int nbgpu_dist_plan_local_cols(const nbgpu_dist_plan_t *plan, uint32_t *cols_local);
 /* what the other ranks need from me (the transpose of their halo lists, which the
  * processes exchange by any means): send_global grouped by destination in the
- * order of the destination's halo list; dst_offsets[d] = position of my block in
- * rank d's halo list */
+ * order of the destination's halo list; dst_offsets[d] = where my block starts in
+ * rank d's COLUMN SPACE (its position in d's halo list mapped through d's
+ * nbgpu_dist_ext_layout) */
 int nbgpu_dist_plan_set_sends(nbgpu_dist_plan_t *plan, const uint32_t *send_counts,
 			      const uint32_t *send_global, const uint32_t *dst_offsets);
 
-/* ext_len >= N_loc + n_halo.  Writes this rank's 64-byte CUDA IPC handle. */
+/* ext_len from nbgpu_dist_plan_layout.  Writes this rank's 64-byte CUDA IPC handle
+ * (ipc_handle_out may be NULL for ranks that connect with nbgpu_dist_connect_local). */
 int nbgpu_dist_create(int rank, int world, size_t ext_len, void *ipc_handle_out,
 		      nbgpu_dist_t **out);
 /* all_handles: world x 64 bytes in rank order; all_ext_len: every rank's ext_len */
 int nbgpu_dist_connect(nbgpu_dist_t *dist, const void *all_handles,
 		       const uint64_t *all_ext_len);
+/* ranks living in ONE process (one host thread per GPU, nbgpu_thread_bind_device):
+ * all[r] = rank r's object, device_of[r] = its GPU; peer access instead of IPC */
+int nbgpu_dist_connect_local(nbgpu_dist_t *dist, nbgpu_dist_t *const *all,
+			     const int *device_of);
 int nbgpu_dist_destroy(nbgpu_dist_t *dist);
 int nbgpu_dist_error(nbgpu_dist_t *dist);
 
@@ -451,10 +490,9 @@ int nbgpu_dist_cg(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
 		  double *tolerance_reached);
 int nbgpu_dist_spmv(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
 		    const nbgpu_matrix_t *A_local, const double *d_in, double *d_out);
-/* device pointer to the window's input vector (N_loc owned entries, halo tail
- * behind them): an SpMV caller that writes x there and passes it as d_in saves
- * the copy into the window */
-double *nbgpu_dist_input_vector(nbgpu_dist_t *dist);
+/* device pointer to the owned part of the window's input vector: an SpMV caller
+ * that writes x there and passes it as d_in saves the copy into the window */
+double *nbgpu_dist_input_vector(nbgpu_dist_t *dist, const nbgpu_dist_plan_t *plan);
 
 #ifdef __cplusplus
 }

@@ -109,7 +109,12 @@ SIGNATURES = {
     "nbgpu_fem_session_step": (C.c_int, [C.c_void_p, u8p, f64p, C.c_int, C.c_uint32, C.c_double, C.c_void_p]),
     "nbgpu_fem_session_results": (C.c_int, [C.c_void_p, f64p, f64p]),
     "nbgpu_fem_session_destroy": (C.c_int, [C.c_void_p]),
-    "nbgpu_matrix_create_local": (C.c_int, [C.c_uint32, C.c_uint32, u32p, u32p, f64p, vpp]),
+    "nbgpu_matrix_create_local": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, f64p, vpp]),
+    "nbgpu_dist_ext_layout": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, u32p]),
+    "nbgpu_dist_plan_layout": (C.c_int, [C.c_void_p, u32p, u32p, u32p, u32p]),
+    "nbgpu_dist_connect_local": (C.c_int, [C.c_void_p, vpp, C.POINTER(C.c_int)]),
+    "nbgpu_set_pcg_mode": (C.c_int, [C.c_int]),
+    "nbgpu_thread_bind_device": (C.c_int, [C.c_int]),
     "nbgpu_dist_plan_create": (C.c_int, [C.c_int, C.c_int, u32p, u32p, u32p, vpp]),
     "nbgpu_dist_plan_destroy": (C.c_int, [C.c_void_p]),
     "nbgpu_dist_plan_info": (C.c_int, [C.c_void_p, u32p, u32p, u64p, u32p]),
@@ -124,7 +129,7 @@ SIGNATURES = {
                                         C.c_double, u32p, f64p]),
     "nbgpu_dist_cg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
                                 u32p, f64p]),
-    "nbgpu_dist_input_vector": (C.c_void_p, [C.c_void_p]),
+    "nbgpu_dist_input_vector": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "nbgpu_dist_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -40,6 +40,7 @@ struct Context {
 	double *partials = nullptr;           // [4][kMaxPartialBlocks] reduction partials
 	void *dev_state = nullptr;            // solver scalars (krylov.cu)
 	void *host_state = nullptr;           // pinned mirror
+	cudaEvent_t poll_ev[2] = {nullptr, nullptr};   // convergence polling (krylov.cu)
 	uint64_t launches = 0;
 	cudaMemPool_t pool = nullptr;         // retained allocation pool (null: plain cudaMalloc)
 };
@@ -196,6 +197,61 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials,
 		out[k] = s;
 	}
 	return true;
+}
+
+// Ticketless form of the same reduction, split over a kernel boundary (single GPU): the producer
+// kernel's CTAs only store their partials (cta_store_partials); every CTA of the CONSUMER kernel
+// sums them itself in a fixed order (cta_sum_partials), so all CTAs get bit-identical totals.  What
+// the producer saves -- fence, ticket atomic, the last CTA re-reading and summing the partials, one
+// more store -- sits on the critical path between two dependent kernels; what the consumer adds is a
+// few coalesced L2 loads where it used to read one scalar (one round trip either way).
+template <int NV>
+__device__ __forceinline__ void cta_store_partials(double (&v)[NV], double *partials)
+{
+	__shared__ double sm[NV][kBlock / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < NV; k++) {
+		double s = warp_sum(v[k]);
+		if (lane == 0)
+			sm[k][warp] = s;
+	}
+	__syncthreads();
+	if (warp == 0) {
+#pragma unroll
+		for (int k = 0; k < NV; k++) {
+			double s = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
+			s = warp_sum(s);
+			if (lane == 0)
+				partials[k * gridDim.x + blockIdx.x] = s;
+		}
+	}
+}
+
+// partials: [NV][n_ctas] as written by a grid of n_ctas CTAs; same summation tree as grid_reduce's last CTA
+template <int NV>
+__device__ __forceinline__ void cta_sum_partials(const double *partials, uint32_t n_ctas, double (&out)[NV])
+{
+	__shared__ double sm[NV][kBlock / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < NV; k++) {
+		double s = 0.0;
+		for (unsigned int b = threadIdx.x; b < n_ctas; b += kBlock)
+			s += __ldcg(partials + k * n_ctas + b);
+		s = warp_sum(s);
+		if (lane == 0)
+			sm[k][warp] = s;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < NV; k++) {
+		double s = 0.0;
+#pragma unroll
+		for (int w = 0; w < kBlock / 32; w++)
+			s += sm[k][w];
+		out[k] = s;
+	}
 }
 
 }  // namespace nbgpu

@@ -8,9 +8,16 @@
 namespace nbgpu {
 
 static thread_local std::string g_error;
-static Context g_ctx;
+// One context per process by default.  A host thread that calls nbgpu_thread_bind_device(d) switches
+// to a context of its own for device d (the single-process multi-GPU mode: one worker thread per GPU,
+// each running the unchanged one-GPU-per-rank code); every other thread keeps the process context.
+constexpr int kMaxDeviceContexts = 16;
+static Context g_default_ctx;
+static Context g_device_ctx[kMaxDeviceContexts];
+static thread_local Context *t_ctx = &g_default_ctx;
+#define g_ctx (*t_ctx)
 
-Context &ctx() { return g_ctx; }
+Context &ctx() { return *t_ctx; }
 
 cudaError_t dmalloc_bytes(void **p, size_t bytes)
 {
@@ -54,7 +61,7 @@ void set_error(const char *fmt, ...)
 
 static int init_device(int device)
 {
-	Context &c = g_ctx;
+	Context &c = *t_ctx;
 	if (c.ready)
 		return NBGPU_OK;
 	int count = 0;
@@ -188,6 +195,10 @@ void l2_unpin()
 	v.accessPolicyWindow.num_bytes = 0;
 	cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &v);
 	cudaCtxResetPersistingL2Cache();
+	// give the carve-out back: left in place it takes 79 of the 126 MB of L2 away from every later
+	// kernel of the process (measured: a 4 M-dof solve after a 1 M-dof one ran at 280 instead of
+	// 164 us per iteration)
+	cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
 	cudaGetLastError();
 }
 
@@ -221,6 +232,8 @@ int nbgpu_finalize(void)
 		if (c.stage[i])
 			cudaFreeHost(c.stage[i]);
 		cudaEventDestroy(c.ev_stage[i]);
+		if (c.poll_ev[i])
+			cudaEventDestroy(c.poll_ev[i]);
 	}
 	if (c.ws)
 		nbgpu::dfree(c.ws);
@@ -293,7 +306,31 @@ void *nbgpu_stream(void)
 	return (void *)g_ctx.stream;
 }
 
-uint64_t nbgpu_launch_count(void) { return g_ctx.launches; }
+uint64_t nbgpu_launch_count(void)
+{
+	uint64_t n = g_default_ctx.launches;
+	for (int d = 0; d < kMaxDeviceContexts; d++)
+		n += g_device_ctx[d].launches;
+	return n;
+}
+
+int nbgpu_thread_bind_device(int device)
+{
+	if (device < 0) {
+		t_ctx = &g_default_ctx;
+		return NBGPU_OK;
+	}
+	NB_ARG(device < kMaxDeviceContexts);
+	t_ctx = &g_device_ctx[device];
+	if (t_ctx->ready) {
+		cudaSetDevice(device);
+		return NBGPU_OK;
+	}
+	const int st = init_device(device);
+	if (st != NBGPU_OK)
+		t_ctx = &g_default_ctx;
+	return st;
+}
 
 int nbgpu_malloc(void **d_ptr, size_t bytes)
 {

@@ -102,9 +102,9 @@ build_bcol_kernel(uint32_t n_slices, const uint32_t *__restrict__ slice_off,
 // int16 differences of the column ids to the row's own index (per-block node ids to the row's node when
 // `blocked`), same positions as the source array; *too_far is raised when one does not fit.
 __global__ void __launch_bounds__(kBlock)
-build_idx16_kernel(bool blocked, uint32_t N, uint32_t n_slices, const uint32_t *__restrict__ slice_off,
-		   const uint32_t *__restrict__ perm, const uint32_t *__restrict__ ids, short *__restrict__ out,
-		   int *too_far)
+build_idx16_kernel(bool blocked, uint32_t N, uint32_t col_shift, uint32_t n_slices,
+		   const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ perm,
+		   const uint32_t *__restrict__ ids, short *__restrict__ out, int *too_far)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -117,7 +117,7 @@ build_idx16_kernel(bool blocked, uint32_t N, uint32_t n_slices, const uint32_t *
 				const uint32_t c = ids[idx];
 				int d = -32768;
 				if (c != kPadCol) {
-					const int64_t diff = (int64_t)c - (int64_t)row;
+					const int64_t diff = (int64_t)c - (int64_t)row - (int64_t)col_shift;
 					if (diff < -32767 || diff > 32767 || row >= N)
 						*too_far = 1;
 					d = (int)diff;
@@ -132,7 +132,7 @@ build_idx16_kernel(bool blocked, uint32_t N, uint32_t n_slices, const uint32_t *
 				const uint32_t c = ids[idx];
 				int d = -32768;
 				if (c != kPadCol) {
-					const int64_t diff = (int64_t)c - (int64_t)(row >> 1);
+					const int64_t diff = (int64_t)c - (int64_t)((row + col_shift) >> 1);
 					if (diff < -32767 || diff > 32767 || row >= N)
 						*too_far = 1;
 					d = (int)diff;
@@ -431,7 +431,7 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 	NB_CUDA(cudaStreamSynchronize(c.copy_stream));   // staged uploads have landed
 	if (A->n_slices) {
 		csr_to_sell_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
-			A->N, A->n_cols, !A->local_block, A->n_slices, (const uint64_t *)rp.p, d_cols, d_vals, A->d_slice_off,
+			A->N, A->n_cols, true, A->n_slices, (const uint64_t *)rp.p, d_cols, d_vals, A->d_slice_off,
 			A->d_perm, d_cols ? A->d_col : nullptr, A->d_val, (int *)bad.p);
 		NB_LAUNCHED();
 	}
@@ -458,12 +458,12 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 			A->blocked = true;
 		}
 	}
-	if (d_cols && A->n_slices && !A->local_block && !getenv("NBGPU_NO_IDX16")) {
+	if (d_cols && A->n_slices && !getenv("NBGPU_NO_IDX16")) {
 		const size_t n_ids = A->blocked ? A->stored / 4 : A->stored;
 		NB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), c.stream));
 		NB_CUDA(nbgpu::dmalloc(&A->d_idx16, std::max<size_t>(1, n_ids) * sizeof(short)));
 		build_idx16_kernel<<<grid_for_slices(A->n_slices), kBlock, 0, c.stream>>>(
-			A->blocked, A->N, A->n_slices, A->d_slice_off, A->d_perm, A->blocked ? A->d_bcol : A->d_col,
+			A->blocked, A->N, A->col_shift, A->n_slices, A->d_slice_off, A->d_perm, A->blocked ? A->d_bcol : A->d_col,
 			A->d_idx16, (int *)bad.p);
 		NB_LAUNCHED();
 		NB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
@@ -597,13 +597,15 @@ int nbgpu_matrix_create_from_csr(uint32_t N, const uint32_t *rows_size, const ui
 	return NBGPU_OK;
 }
 
-int nbgpu_matrix_create_local(uint32_t N_rows, uint32_t N_cols, const uint32_t *rows_size,
+int nbgpu_matrix_create_local(uint32_t N_rows, uint32_t N_cols, uint32_t col_shift, const uint32_t *rows_size,
 			      const uint32_t *cols_local, const double *vals, nbgpu_matrix_t **out)
 {
 	NB_INIT();
-	NB_ARG(out != nullptr && N_cols >= N_rows && (N_rows == 0 || (rows_size != nullptr && cols_local != nullptr)));
+	NB_ARG(out != nullptr && (uint64_t)col_shift + N_rows <= N_cols && (col_shift & 1u) == 0 &&
+	       (N_rows == 0 || (rows_size != nullptr && cols_local != nullptr)));
 	nbgpu_matrix_t *A = new nbgpu_matrix_t();
 	A->n_cols = N_cols;
+	A->col_shift = col_shift;
 	A->local_block = true;
 	int st = build_layout(A, N_rows, rows_size);
 	DeviceTemp dc, dv;

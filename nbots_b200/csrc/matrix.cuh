@@ -19,9 +19,10 @@
 
 struct nbgpu_matrix_s {
 	uint32_t N = 0;                       // rows
-	uint32_t n_cols = 0;                  // column space (== N except for a rank-local block, which
-					      // appends its halo columns after the owned ones)
-	bool local_block = false;             // columns are local ids in ascending GLOBAL order: not sorted
+	uint32_t n_cols = 0;                  // column space (== N except for a rank-local block)
+	bool local_block = false;             // rank-local block of a partitioned matrix (dist.cu): column space
+					      // "lower halo | owned | upper halo" of n_cols entries
+	uint32_t col_shift = 0;               // ... in which row r is column r + col_shift
 	uint64_t nnz = 0;
 	uint32_t n_slices = 0;
 	uint64_t stored = 0;                  // padded entry count = 32 * slice_off[n_slices]

@@ -36,6 +36,8 @@
 // targets made the kernel 17 % slower (28 KB of L1 left beside the stages).
 #pragma once
 
+#include <type_traits>
+
 #include "spmv.cuh"
 
 namespace nbgpu {
@@ -98,6 +100,26 @@ __device__ __forceinline__ double2 ld_gather_f64x2(const double *p)
 	return r;
 }
 
+// Gathers of a vector whose halo part is written by PEER GPUs while the kernel runs (dist.cu): `.nc`
+// is only defined for data that stays read-only for the kernel's lifetime, and a non-coherent L1 line
+// could outlive the arrival of a halo.  Slices that read halo columns (visited last, after the
+// acquire of the neighbours' flags) therefore gather with `ld.relaxed.gpu` -- a strong load, served
+// from L2, the point of coherence for NVLink stores into this GPU's memory; all other slices keep
+// the read-only path.  The halo parts of such a vector start on their own 128-byte lines
+// (nbgpu_dist_ext_layout), so an interior slice can never pull a stale halo value into L1.
+__device__ __forceinline__ double ld_gather_f64_coherent(const double *p)
+{
+	double r;
+	asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(r) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ double2 ld_gather_f64x2_coherent(const double *p)
+{
+	double2 r;
+	asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+	return r;
+}
+
 // ------------------------------------------------------------- geometry ----
 constexpr int kStreamWarps = kBlock / 32;      // consumer warps per CTA
 #ifndef NB_STREAM_CTAS
@@ -140,6 +162,9 @@ struct SellView {
 	uint32_t visit_shift = 0;
 	uint32_t late_from = 0xFFFFFFFFu;
 	uint32_t uniform_width = 0;   // != 0: slice s starts at s * uniform_width (no offset loads)
+	// rank-local block (HALO kernels): row r is column r + col_shift of the block's column space
+	// "lower halo | owned | upper halo" (even, a multiple of 16)
+	uint32_t col_shift = 0;
 	const uint32_t *perm = nullptr;   // SELL-C-sigma: row stored at position slice * 32 + lane (null: identity)
 };
 
@@ -157,10 +182,21 @@ struct SellView {
 // false the warp only drains its in-flight copies and leaves.  `late()` is
 // called once, before the first slice with visit index >= A.late_from (slices
 // that need data a peer GPU is still sending); false = give up likewise.
-template <bool BLOCKED, bool WANT_DIAG, bool IDX16, typename Gate, typename Late, typename Body>
-__device__ __forceinline__ void sell_stream_rows(const SellView A, const double *__restrict__ x,
+// `pre(row)` runs when a slice's stage has landed, BEFORE its gathers: a load the body needs (one
+// more row-indexed vector) is issued there so that its latency hides behind the gathers; its value
+// is handed to `body(row, acc, diag, x_row, pre_value)`.
+// HALO: x is the extended vector of a rank-local block (col_shift, coherent gathers for the late
+// slices, see ld_gather_f64_coherent).  After the gate every CTA releases its programmatic dependents, so
+// the next kernel's CTAs become resident (and run their pre-wait loads) as this kernel's CTAs retire.
+struct NoPre {
+	__device__ __forceinline__ double operator()(uint32_t) const { return 0.0; }
+};
+
+template <bool BLOCKED, bool WANT_DIAG, bool IDX16, bool HALO, typename Gate, typename Late, typename Pre,
+	  typename Body>
+__device__ __forceinline__ void sell_stream_rows(const SellView A, const double *x,
 						 const StreamConfig cfg, unsigned char *smem, Gate gate, Late late,
-						 Body body)
+						 Pre pre, Body body)
 {
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t total_warps = gridDim.x * kStreamWarps;
@@ -221,13 +257,16 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		}
 	__syncwarp();
 	pdl_wait();
-	if (!gate()) {
+	const bool go = gate();
+	pdl_launch_dependents();
+	if (!go) {
 		// a CTA must not exit with bulk copies still landing in its shared memory
 		for (uint32_t st = 0; st < cfg.stages; st++)
 			if ((uint64_t)first + (uint64_t)st * total_warps < A.n_slices)
 				mbar_wait(bars + st, 0);
 		return;
 	}
+	const uint32_t col_shift = HALO ? A.col_shift : 0u;
 
 	uint32_t n = 0;
 	bool late_done = false;
@@ -257,6 +296,13 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			}
 		}
 		mbar_wait(bars + st, parity);
+		// The work on one slice, compiled twice for HALO kernels: slices that read halo columns gather
+		// coherently (see ld_gather_f64_coherent), all others through the read-only path.  (One body with
+		// a run-time choice of the load instruction per gather cost 100-200 bytes of register spills.)
+		auto slice_work = [&](auto coh_tag) {
+		constexpr bool kCoh = decltype(coh_tag)::value;
+		const double pre_value = pre(row);
+		const uint32_t crow = row + col_shift;   // this row's index in the column space
 		const uint2 m = meta[st];
 		const uint32_t width = m.y;
 		const unsigned char *stage = ring + (size_t)st * cfg.stage_bytes;
@@ -280,7 +326,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		// keeps two copies per warp in flight instead of one (the kernel is bound by bytes in flight).
 		// id k of this lane: entry column k, or block k of the lane's node pair when BLOCKED
 		const unsigned char *sids = stage + (size_t)cfg.cap * val_bytes_per_col;
-		const uint32_t id_base = BLOCKED ? (row >> 1) : row;
+		const uint32_t id_base = BLOCKED ? (crow >> 1) : crow;
 		auto load_id = [&](uint32_t k) -> uint32_t {
 			constexpr uint32_t kStride = BLOCKED ? 16u : kSliceRows;
 			const uint32_t mine = BLOCKED ? (lane >> 1) : lane;
@@ -290,6 +336,8 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			}
 			return reinterpret_cast<const uint32_t *>(sids)[k * kStride + mine];
 		};
+		auto gather1 = [&](const double *p) { return kCoh ? ld_gather_f64_coherent(p) : ld_gather_f64(p); };
+		auto gather2 = [&](const double *p) { return kCoh ? ld_gather_f64x2_coherent(p) : ld_gather_f64x2(p); };
 #ifndef NB_EARLY
 #define NB_EARLY 2
 #endif
@@ -304,7 +352,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				cj[u] = (uint32_t)u < width ? load_id(u) : kPadCol;
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++)
-				xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? 0u : cj[u]));
+				xj[u] = gather1(x + (cj[u] == kPadCol ? 0u : cj[u]));
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++)
 				vj[u] = (uint32_t)u < width ? sval[u * kSliceRows] : 0.0;
@@ -313,7 +361,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			for (int u = 0; u < kGatherBatch; u++) {
 				const double t = __dmul_rn(vj[u], xj[u]);
 				acc = (cj[u] == kPadCol) ? acc : __dadd_rn(acc, t);
-				if (cj[u] == row) {
+				if (cj[u] == crow) {
 					diag = vj[u];
 					x_row = xj[u];
 					have_row = true;
@@ -321,7 +369,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			}
 		} else if (BLOCKED && single) {
 			const uint32_t nblk = width >> 1;
-			const uint32_t my_node = row >> 1;
+			const uint32_t my_node = crow >> 1;
 			uint32_t cb[kGatherBatch];
 			double2 xb[kGatherBatch];
 			double v0[kGatherBatch], v1[kGatherBatch];
@@ -330,7 +378,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				cb[u] = (uint32_t)u < nblk ? load_id(u) : kPadCol;
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++)
-				xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
+				xb[u] = gather2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
 #pragma unroll
 			for (int u = 0; u < kGatherBatch; u++) {
 				v0[u] = (uint32_t)u < nblk ? sval[(2 * u) * kSliceRows] : 0.0;
@@ -363,14 +411,14 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 					cj[u] = load_id(j0 + u);
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					xj[u] = ld_gather_f64(x + (cj[u] == kPadCol ? 0u : cj[u]));
+					xj[u] = gather1(x + (cj[u] == kPadCol ? 0u : cj[u]));
 				__syncwarp();
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++) {
 					const double v = sval[(j0 + u) * kSliceRows];
 					const double t = __dmul_rn(v, xj[u]);
 					acc = (cj[u] == kPadCol) ? acc : __dadd_rn(acc, t);
-					if (cj[u] == row) {
+					if (cj[u] == crow) {
 						diag = v;
 						x_row = xj[u];
 						have_row = true;
@@ -380,10 +428,10 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			for (; j0 < width; j0++) {
 				const uint32_t cj = load_id(j0);
 				const double v = sval[j0 * kSliceRows];
-				const double xj = ld_gather_f64(x + (cj == kPadCol ? 0u : cj));
+				const double xj = gather1(x + (cj == kPadCol ? 0u : cj));
 				const double t = __dmul_rn(v, xj);
 				acc = (cj == kPadCol) ? acc : __dadd_rn(acc, t);
-				if (cj == row) {
+				if (cj == crow) {
 					diag = v;
 					x_row = xj;
 					have_row = true;
@@ -392,7 +440,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		} else {
 			// one node id per 2x2 block; lanes 2k, 2k+1 (the two dofs of a node) share it
 			const uint32_t nblk = width >> 1;
-			const uint32_t my_node = row >> 1;
+			const uint32_t my_node = crow >> 1;
 			uint32_t b0 = 0;
 			for (; b0 + kGatherBatch <= nblk; b0 += kGatherBatch) {
 				uint32_t cb[kGatherBatch];
@@ -402,7 +450,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 					cb[u] = load_id(b0 + u);
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++)
-					xb[u] = ld_gather_f64x2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
+					xb[u] = gather2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
 				__syncwarp();
 #pragma unroll
 				for (int u = 0; u < kGatherBatch; u++) {
@@ -423,7 +471,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			for (; b0 < nblk; b0++) {
 				const uint32_t cb = load_id(b0);
 				const double v0 = sval[(2 * b0) * kSliceRows], v1 = sval[(2 * b0 + 1) * kSliceRows];
-				const double2 xb = ld_gather_f64x2(x + 2 * (size_t)(cb == kPadCol ? 0u : cb));
+				const double2 xb = gather2(x + 2 * (size_t)(cb == kPadCol ? 0u : cb));
 				const bool pad = cb == kPadCol;
 				const double t0 = __dmul_rn(v0, xb.x);
 				acc = pad ? acc : __dadd_rn(acc, t0);
@@ -439,8 +487,13 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		if (!single)
 			release();
 		if (!have_row && row < A.N)
-			x_row = __ldg(x + row);   // row without a stored diagonal
-		body(row, acc, diag, x_row);
+			x_row = gather1(x + crow);   // row without a stored diagonal
+		body(row, acc, diag, x_row, pre_value);
+		};   // slice_work
+		if (HALO && s64 >= A.late_from)
+			slice_work(std::true_type{});
+		else
+			slice_work(std::false_type{});
 	}
 }
 

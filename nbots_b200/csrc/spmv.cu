@@ -32,10 +32,12 @@ __global__ void __launch_bounds__(kBlock, kStreamCtas)
 spmv_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ x, double *__restrict__ y)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	sell_stream_rows<(LAYOUT & 1) != 0, false, (LAYOUT & 2) != 0>(A, x, cfg, smem, [] { return true; }, [] { return true; }, [&](uint32_t row, double acc, double, double) {
-		if (row < A.N)
-			y[row] = acc;
-	});
+	sell_stream_rows<(LAYOUT & 1) != 0, false, (LAYOUT & 2) != 0, false>(
+		A, x, cfg, smem, [] { return true; }, [] { return true; }, NoPre(),
+		[&](uint32_t row, double acc, double, double, double) {
+			if (row < A.N)
+				y[row] = acc;
+		});
 }
 
 // Ring depth and CTAs per SM for the streamed kernels of matrix A.  Shared memory
@@ -113,6 +115,9 @@ int nbgpu_spmv(const nbgpu_matrix_t *A, const double *d_in, double *d_out)
 	NB_INIT();
 	NB_ARG(A != nullptr && d_in != nullptr && d_out != nullptr);
 	NB_ARG(d_in != d_out);   /* the reference accumulates into out[]: no aliasing (sparse.c:410) */
+	NB_ARG(!A->local_block);   /* rank-local blocks go through nbgpu_dist_spmv */
+	/* the blocked layout gathers x[2c], x[2c+1] as one 16-byte load */
+	NB_ARG(!A->blocked || ((uintptr_t)d_in & 15) == 0);
 	if (A->N == 0)
 		return NBGPU_OK;
 	StreamConfig cfg;

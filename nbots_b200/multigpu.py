@@ -126,19 +126,23 @@ class DistContext:
         check(L.nbgpu_dist_plan_info(self.plan, C.byref(n_loc), C.byref(n_halo), C.byref(nnz),
                                      recv_counts.ctypes.data_as(u32p)))
         self.N_loc, self.n_halo, self.recv_counts = n_loc.value, n_halo.value, recv_counts
+        n_lo = C.c_uint32(); off_own = C.c_uint32(); off_up = C.c_uint32(); ext_len = C.c_uint32()
+        check(L.nbgpu_dist_plan_layout(self.plan, C.byref(n_lo), C.byref(off_own), C.byref(off_up), C.byref(ext_len)))
+        # column space of the rank-local block: lower halo | owned | upper halo (nbgpu_dist_ext_layout)
+        self.n_lo, self.off_own, self.off_up, self.ext_len = n_lo.value, off_own.value, off_up.value, ext_len.value
         halo = np.zeros(max(1, self.n_halo), dtype=np.uint32)
         check(L.nbgpu_dist_plan_halo_ids(self.plan, halo.ctypes.data_as(u32p)))
         self.halo_global = halo[:self.n_halo]
         # every rank learns what every other rank needs (small lists: the cut lines)
-        everyone = gather_obj((recv_counts, self.halo_global))
+        everyone = gather_obj((recv_counts, self.halo_global, self.n_lo, self.off_up))
         send_counts = np.zeros(world, dtype=np.uint32)
         dst_offsets = np.zeros(world, dtype=np.uint32)
         send_lists = []
-        for d, (rc, hg) in enumerate(everyone):
-            off = int(rc[:rank].sum())
+        for d, (rc, hg, n_lo_d, off_up_d) in enumerate(everyone):
+            off = int(rc[:rank].sum())                       # position of my block in rank d's halo list ...
             cnt = int(rc[rank])
             send_counts[d] = cnt
-            dst_offsets[d] = off
+            dst_offsets[d] = off if off < n_lo_d else off_up_d + (off - n_lo_d)   # ... and in its column space
             send_lists.append(np.asarray(hg[off:off + cnt], dtype=np.uint32))
         send_global = np.concatenate(send_lists) if send_lists else np.zeros(0, np.uint32)
         send_global = np.ascontiguousarray(send_global, dtype=np.uint32)
@@ -159,10 +163,10 @@ class DistContext:
         L = lib()
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         h = C.c_void_p()
-        check(L.nbgpu_matrix_create_local(self.N_loc, self.N_loc + self.n_halo, self.rows_size.ctypes.data_as(u32p),
+        check(L.nbgpu_matrix_create_local(self.N_loc, self.ext_len, self.off_own, self.rows_size.ctypes.data_as(u32p),
                                           self.cols_local.ctypes.data_as(u32p), vals.ctypes.data_as(f64p), C.byref(h)))
         self.A = api.Matrix(h.value)
-        ext_len = self.N_loc + self.n_halo
+        ext_len = self.ext_len
         handle = (C.c_char * 64)()
         dh = C.c_void_p()
         check(L.nbgpu_dist_create(self.rank, self.world, ext_len, handle, C.byref(dh)))
@@ -260,6 +264,19 @@ def bench(args, rank, world, dist):
     ms_step = float(np.mean(times))
     value = N_global * iters / (ms_step * 1e-3)
 
+    # per-kernel CUDA-event times of 256 iterations (rank 0's view)
+    check(L.nbgpu_krylov_profile(1))
+    check(L.nbgpu_memset(d_x.ptr, 0, N_loc * 8))
+    barrier()
+    dc.pcg_jacobi(d_b, d_x, 256, 0.0)
+    check(L.nbgpu_krylov_profile(0))
+    ms3 = np.zeros(3); n_prof = C.c_uint32(0)
+    check(L.nbgpu_krylov_profile_get(ms3.ctypes.data_as(f64p), C.byref(n_prof)))
+    kernel_us = [round(float(v) / max(1, n_prof.value) * 1e3, 2) for v in ms3]
+    check(L.nbgpu_memset(d_x.ptr, 0, N_loc * 8))
+    barrier()
+    dc.pcg_jacobi(d_b, d_x, N_global, tol)
+
     # e2e: host-resident block of the matrix and host vectors on every rank, all copies timed
     x_host = np.zeros(N_loc)
     e2e_times = []
@@ -267,7 +284,7 @@ def bench(args, rank, world, dist):
         barrier()
         t0 = time.perf_counter()
         h = C.c_void_p()
-        check(L.nbgpu_matrix_create_local(dc.N_loc, dc.N_loc + dc.n_halo, dc.rows_size.ctypes.data_as(u32p),
+        check(L.nbgpu_matrix_create_local(dc.N_loc, dc.ext_len, dc.off_own, dc.rows_size.ctypes.data_as(u32p),
                                           dc.cols_local.ctypes.data_as(u32p), prob.vals.ctypes.data_as(f64p),
                                           C.byref(h)))
         A2 = api.Matrix(h.value)
@@ -298,6 +315,9 @@ def bench(args, rank, world, dist):
                            "rel_tol": B.REL_TOL, "dof_per_gpu": int(N_loc), "halo_values_per_rank": int(dc.n_halo),
                            "exchange": "NVLink peer stores + sequence flags (CUDA IPC windows); no NCCL in the loop",
                            "l2": "per-GPU working set 265 MB exceeds the 126 MB L2; no flush",
+                           "local_block_layout": {"blocked": dc.A.blocked, "idx16": dc.A.idx16,
+                                                  "uniform_width": dc.A.uniform_width},
+                           "kernel_us_rank0": kernel_us, "us_per_iteration": round(ms_step * 1e3 / iters, 2),
                            "setup_s": round(t_setup, 2)},
                 "roofline": {"bound": "hbm", "kernel": "whole iteration (dist_spmv + dist_update + dist_dir + halo_push)",
                              "achieved": round(bytes_iter * iters / (ms_step * 1e-3) / 1e9 / world, 1),

@@ -51,6 +51,15 @@ def run_cpu(rank, world):
     assert np.array_equal(np.sort(np.unique(cols[rp[r0]:rp[r1]][(cols[rp[r0]:rp[r1]] < r0) | (cols[rp[r0]:rp[r1]] >= r1)])),
                           dc.halo_global)
     A_loc = port.Csr(rs[r0:r1], dc.cols_local, vals[rp[r0]:rp[r1]])       # local ids, entry order untouched
+    # column space "lower halo | owned | upper halo": local ids ascend like the global ones, parts on 128-byte lines
+    assert dc.off_own % 16 == 0 and dc.off_up % 16 == 0 and dc.ext_len % 16 == 0
+    assert dc.n_lo == int((dc.halo_global < r0).sum()) and dc.off_own >= dc.n_lo
+    assert dc.off_up >= dc.off_own + dc.N_loc and dc.ext_len >= dc.off_up + (dc.n_halo - dc.n_lo)
+    glob = cols[rp[r0]:rp[r1]].astype(np.int64)
+    want = np.where(glob < r0, np.searchsorted(dc.halo_global, glob),
+                    np.where(glob < r1, dc.off_own + glob - r0,
+                             dc.off_up + np.searchsorted(dc.halo_global, glob) - dc.n_lo))
+    assert np.array_equal(dc.cols_local, want.astype(np.uint32))
 
     def exchange(v_loc):
         """halo of a distributed vector: what nbots_b200/csrc/dist.cu does with peer stores, here over gloo"""
@@ -60,15 +69,15 @@ def run_cpu(rank, world):
             cnt = int(dc.send_counts[d])
             sends.append(v_loc[dc.send_global[off:off + cnt] - r0].copy())
             off += cnt
-        everyone = gather(sends)
-        ext = np.zeros(dc.N_loc + dc.n_halo)
-        ext[:dc.N_loc] = v_loc
-        pos = dc.N_loc
+        everyone = gather((sends, dc.dst_offsets))
+        ext = np.full(dc.ext_len, np.nan)                  # padding must never be read
+        ext[dc.off_own:dc.off_own + dc.N_loc] = v_loc
         for src in range(world):
-            chunk = everyone[src][rank]
+            chunk = everyone[src][0][rank]
             assert chunk.size == dc.recv_counts[src]
+            pos = int(everyone[src][1][rank])              # where rank src's kernels store into my ext vector
             ext[pos:pos + chunk.size] = chunk
-            pos += chunk.size
+        assert not np.isnan(ext[:dc.n_lo]).any() and not np.isnan(ext[dc.off_up:dc.off_up + dc.n_halo - dc.n_lo]).any()
         return ext
 
     def allsum(*vals_):
