@@ -494,6 +494,62 @@ int nbgpu_dist_spmv(nbgpu_dist_t *dist, nbgpu_dist_plan_t *plan,
  * that writes x there and passes it as d_in saves the copy into the window */
 double *nbgpu_dist_input_vector(nbgpu_dist_t *dist, const nbgpu_dist_plan_t *plan);
 
+/* ---------------------------------------- multi-GPU FEM (row slabs) -- */
+/* nb_fem_compute_2D_Solid_Mechanics (static_elasticity2D.c:31-97) on a mesh
+ * partitioned into contiguous NODE ranges, one rank per GPU: every rank gets the
+ * whole mesh description, integrates the sub-mesh of all elements that touch its
+ * nodes straight into its rank-local block ON THE DEVICE (elements on a cut are
+ * integrated on both sides: no communication, K never visits the host), applies
+ * the boundary conditions restricted to its rows, and the ranks solve together.
+ * The rank-local rows are bit-identical to the rows of the single-GPU matrix.
+ * All halo / send lists are derived locally from the mesh: the ranks exchange
+ * only the 64-byte IPC handles (nbgpu_dist_fem_connect), or nothing when they
+ * live in one process (nbgpu_dist_fem_connect_local). */
+typedef struct nbgpu_dist_fem_s nbgpu_dist_fem_t;
+
+/* balanced contiguous node ranges, node_starts[world + 1]; boundaries fall on
+ * multiples of `align` nodes (nodes per grid line => slabs of whole lines) */
+int nbgpu_partition_nodes(uint32_t N_nod, int world, uint32_t align,
+			  uint32_t *node_starts);
+/* boundary-condition lists: GLOBAL dof ids, ordered, as nbgpu_bcond_flatten
+ * produces them.  ipc_handle_out (64 bytes) may be NULL for in-process ranks. */
+int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *mesh, int rank, int world,
+			  const uint32_t *node_starts,
+			  const nbgpu_elem_tables_t *tables, const double D[4],
+			  double density, uint32_t n_neumann,
+			  const uint32_t *neumann_dof, const double *neumann_add,
+			  uint32_t n_dirichlet, const uint32_t *dirichlet_dof,
+			  const double *dirichlet_val, int self_weight,
+			  const double gravity[2], double thickness,
+			  void *ipc_handle_out, nbgpu_dist_fem_t **out);
+int nbgpu_dist_fem_destroy(nbgpu_dist_fem_t *fem);
+int nbgpu_dist_fem_info(const nbgpu_dist_fem_t *fem, uint32_t *N_loc,
+			uint64_t *nnz_loc, uint32_t *n_halo, uint32_t *n_elems_loc,
+			uint64_t *ext_len, double *ms_setup);
+int nbgpu_dist_fem_connect(nbgpu_dist_fem_t *fem, const void *all_handles,
+			   const uint64_t *all_ext_len);
+int nbgpu_dist_fem_connect_local(nbgpu_dist_fem_t *fem,
+				 nbgpu_dist_fem_t *const *all,
+				 const int *device_of);
+/* pipeline_assemble_system (pipeline.c:42-73) + nb_fem_set_bconditions
+ * (set_bconditions.c:52-61) for this rank's rows; enabled / elem_scale are the
+ * GLOBAL per-element arrays or NULL.  0, or 1 = distorted element (lowest
+ * global id of this rank's sub-mesh in *first_bad). */
+int nbgpu_dist_fem_assemble(nbgpu_dist_fem_t *fem, const uint8_t *enabled,
+			    const double *elem_scale, uint32_t *first_bad);
+/* collective Jacobi-PCG; max_iter 0 = global N, tolerance <= 0 = 1e-8 */
+int nbgpu_dist_fem_solve(nbgpu_dist_fem_t *fem, int warm_start,
+			 uint32_t max_iter, double tolerance,
+			 uint32_t *niter_performed, double *tolerance_reached);
+/* displacements of this rank's nodes: 2 * (node_starts[rank+1] - node_starts[rank]) */
+int nbgpu_dist_fem_results(nbgpu_dist_fem_t *fem, double *displacement_owned);
+/* the objects behind it (owned by fem) */
+nbgpu_matrix_t *nbgpu_dist_fem_matrix(nbgpu_dist_fem_t *fem);
+nbgpu_dist_plan_t *nbgpu_dist_fem_plan(nbgpu_dist_fem_t *fem);
+nbgpu_dist_t *nbgpu_dist_fem_dist(nbgpu_dist_fem_t *fem);
+double *nbgpu_dist_fem_rhs(nbgpu_dist_fem_t *fem);        /* device, N_loc */
+double *nbgpu_dist_fem_solution(nbgpu_dist_fem_t *fem);   /* device, N_loc */
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,21 @@ class BCond(C.Structure):
 
 BCFUNC = C.CFUNCTYPE(None, f64p, C.c_double, f64p)
 
+
+class MeshDesc(C.Structure):
+    """nbgpu_mesh_desc_t: flat view of a mesh (include/nbgpu.h)."""
+    _fields_ = [("N_nod", C.c_uint32), ("nod", f64p), ("N_elems", C.c_uint32), ("npe", C.c_uint32),
+                ("adj", u32p), ("N_edg", C.c_uint32), ("edg", u32p), ("N_vtx", C.c_uint32),
+                ("vtx", u32p), ("N_sgm", C.c_uint32), ("sgm_sizes", u32p), ("sgm_nodes", u32p)]
+
+    @classmethod
+    def of(cls, m):
+        p = lambda a, t: a.ctypes.data_as(t)  # noqa: E731
+        d = cls(m.n_nod, p(m.nod, f64p), m.n_elems, m.npe, p(m.adj, u32p), m.n_edg, p(m.edg, u32p),
+                m.vtx.size, p(m.vtx, u32p), m.sgm_sizes.size, p(m.sgm_sizes, u32p), p(m.sgm_nodes, u32p))
+        d._keep = m
+        return d
+
 # name -> (restype, argtypes); every symbol declared in include/nbgpu.h
 SIGNATURES = {
     "nbgpu_init": (C.c_int, [C.c_int]),
@@ -131,6 +146,22 @@ SIGNATURES = {
                                 u32p, f64p]),
     "nbgpu_dist_input_vector": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "nbgpu_dist_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nbgpu_partition_nodes": (C.c_int, [C.c_uint32, C.c_int, C.c_uint32, u32p]),
+    "nbgpu_dist_fem_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, C.c_void_p, f64p, C.c_double, C.c_uint32,
+                                        u32p, f64p, C.c_uint32, u32p, f64p, C.c_int, f64p, C.c_double, C.c_void_p,
+                                        vpp]),
+    "nbgpu_dist_fem_destroy": (C.c_int, [C.c_void_p]),
+    "nbgpu_dist_fem_info": (C.c_int, [C.c_void_p, u32p, u64p, u32p, u32p, u64p, f64p]),
+    "nbgpu_dist_fem_connect": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
+    "nbgpu_dist_fem_connect_local": (C.c_int, [C.c_void_p, vpp, C.POINTER(C.c_int)]),
+    "nbgpu_dist_fem_assemble": (C.c_int, [C.c_void_p, u8p, f64p, u32p]),
+    "nbgpu_dist_fem_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_double, u32p, f64p]),
+    "nbgpu_dist_fem_results": (C.c_int, [C.c_void_p, f64p]),
+    "nbgpu_dist_fem_matrix": (C.c_void_p, [C.c_void_p]),
+    "nbgpu_dist_fem_plan": (C.c_void_p, [C.c_void_p]),
+    "nbgpu_dist_fem_dist": (C.c_void_p, [C.c_void_p]),
+    "nbgpu_dist_fem_rhs": (C.c_void_p, [C.c_void_p]),
+    "nbgpu_dist_fem_solution": (C.c_void_p, [C.c_void_p]),
 }
 
 _lib = None

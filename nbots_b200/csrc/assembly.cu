@@ -126,7 +126,8 @@ __device__ __forceinline__ size_t find_in_row(const uint32_t *__restrict__ col, 
 // ---- GATHER: one thread per matrix row -------------------------------------
 template <int NPE, int NGP>
 __global__ void __launch_bounds__(kBlock)
-assemble_gather_kernel(uint32_t N_nod, const double *__restrict__ nod, const uint32_t *__restrict__ adj,
+assemble_gather_kernel(uint32_t n_rows, uint32_t col_shift, const double *__restrict__ nod,
+		       const uint32_t *__restrict__ adj,
 		       const uint32_t *__restrict__ n2e_ptr, const uint32_t *__restrict__ n2e,
 		       const uint8_t *__restrict__ enabled, const double *__restrict__ scale, AsmParams P,
 		       const uint32_t *__restrict__ slice_off, const uint32_t *__restrict__ perm,
@@ -135,13 +136,15 @@ assemble_gather_kernel(uint32_t N_nod, const double *__restrict__ nod, const uin
 {
 	// thread = storage position (slice * 32 + lane), so that the value stores stay coalesced
 	// whatever the row order of the layout is
+	// Rank-local block (dist_fem.cu): the mesh is the sub-mesh numbered like the block's column
+	// space, row r belongs to node (r + col_shift) / 2 of it; otherwise col_shift = 0.
 	const uint32_t spos = blockIdx.x * blockDim.x + threadIdx.x;
-	if (spos >= ((2 * N_nod + kSliceRows - 1) / kSliceRows) * kSliceRows)
+	if (spos >= ((n_rows + kSliceRows - 1) / kSliceRows) * kSliceRows)
 		return;
 	const uint32_t row = perm ? perm[spos] : spos;
-	if (row >= 2 * N_nod)
+	if (row >= n_rows)
 		return;
-	const uint32_t node = row >> 1, a = row & 1, lane = spos & 31;
+	const uint32_t node = (row + col_shift) >> 1, a = row & 1, lane = spos & 31;
 	const uint32_t off = slice_off[spos >> 5], width = slice_off[(spos >> 5) + 1] - off;
 	double f_acc = 0.0;
 	for (uint32_t t = n2e_ptr[node]; t < n2e_ptr[node + 1]; t++) {
@@ -338,7 +341,7 @@ __global__ void vector_add_entries_kernel(double *F, uint32_t n, const uint32_t 
 //                       F[i] -= A_ic * v_first[c], subtracted in the order the
 //                       constraints were applied (ascending order[c]).
 __global__ void __launch_bounds__(kBlock)
-dirichlet_kernel(uint32_t N, uint32_t n_pos, const uint32_t *__restrict__ slice_off,
+dirichlet_kernel(uint32_t N, uint32_t col_shift, uint32_t n_pos, const uint32_t *__restrict__ slice_off,
 		 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ col,
 		 double *__restrict__ val, double *__restrict__ F, const uint32_t *__restrict__ order,
 		 const double *__restrict__ v_first, const double *__restrict__ v_last)
@@ -353,13 +356,14 @@ dirichlet_kernel(uint32_t N, uint32_t n_pos, const uint32_t *__restrict__ slice_
 	const uint32_t off = slice_off[spos >> 5], width = slice_off[(spos >> 5) + 1] - off;
 	const uint32_t *cp = col + (size_t)off * kSliceRows + lane;
 	double *vp = val + (size_t)off * kSliceRows + lane;
-	const uint32_t my = order[row];
+	// `order` is indexed by COLUMN (rank-local block: row r is column r + col_shift)
+	const uint32_t my = order[row + col_shift];
 	if (my) {
 		for (uint32_t j = 0; j < width; j++) {
 			const uint32_t c = cp[(size_t)j * kSliceRows];
 			if (c == kPadCol)
 				break;
-			vp[(size_t)j * kSliceRows] = (c == row) ? 1.0 : 0.0;
+			vp[(size_t)j * kSliceRows] = (c == row + col_shift) ? 1.0 : 0.0;
 		}
 		F[row] = v_last[my - 1];
 		return;
@@ -596,7 +600,7 @@ int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int 
 	if (mode == NBGPU_ASSEMBLY_GATHER) {
 		const uint32_t rows = K->n_slices * kSliceRows;
 		assemble_gather_kernel<NPE, NGP><<<(rows + kBlock - 1) / kBlock, kBlock, 0, c.stream>>>(
-			m->N_nod, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, P, K->d_slice_off,
+			K->N, K->col_shift, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, P, K->d_slice_off,
 			K->d_perm, K->d_col, K->d_val, d_F, d_bad, d_miss);
 		NB_LAUNCHED();
 	} else if (mode == NBGPU_ASSEMBLY_ATOMIC) {
@@ -775,8 +779,10 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
 	NB_INIT();
 	nbgpu_mesh_t *m = const_cast<nbgpu_mesh_t *>(mesh_c);
 	NB_ARG(K != nullptr && m != nullptr && params != nullptr && d_F != nullptr);
-	NB_ARG(K->N == 2 * m->N_nod);
+	NB_ARG(K->local_block ? K->n_cols == 2 * m->N_nod : K->N == 2 * m->N_nod);
 	NB_ARG(params->mode >= NBGPU_ASSEMBLY_GATHER && params->mode <= NBGPU_ASSEMBLY_COLOR);
+	/* rank-local blocks: the row-parallel schedule only (element-parallel scatter would hit ghost rows) */
+	NB_ARG(!K->local_block || params->mode == NBGPU_ASSEMBLY_GATHER);
 	Context &c = ctx();
 	NB_TRY(upload_tables(tables, m->npe));
 	AsmParams P;
@@ -935,12 +941,12 @@ int nbgpu_dirichlet_create(uint32_t N, uint32_t n, const uint32_t *dof, const do
 int nbgpu_dirichlet_apply(nbgpu_matrix_t *K, double *d_F, const nbgpu_dirichlet_t *bc)
 {
 	NB_INIT();
-	NB_ARG(K != nullptr && d_F != nullptr && bc != nullptr && bc->N == K->N);
+	NB_ARG(K != nullptr && d_F != nullptr && bc != nullptr && bc->N == K->n_cols);
 	if (bc->m == 0)
 		return NBGPU_OK;
 	const uint32_t n_pos = K->n_slices * kSliceRows;
 	dirichlet_kernel<<<(n_pos + kBlock - 1) / kBlock, kBlock, 0, ctx().stream>>>(
-		K->N, n_pos, K->d_slice_off, K->d_perm, K->d_col, K->d_val, d_F, bc->d_order, bc->d_first, bc->d_last);
+		K->N, K->col_shift, n_pos, K->d_slice_off, K->d_perm, K->d_col, K->d_val, d_F, bc->d_order, bc->d_first, bc->d_last);
 	NB_LAUNCHED();
 	return NBGPU_OK;
 }
@@ -953,7 +959,7 @@ int nbgpu_apply_dirichlet(nbgpu_matrix_t *K, double *d_F, uint32_t n, const uint
 		return NBGPU_OK;
 	NB_ARG(K != nullptr && d_F != nullptr && dof != nullptr && value != nullptr);
 	nbgpu_dirichlet_t *bc = nullptr;
-	NB_TRY(nbgpu_dirichlet_create(K->N, n, dof, value, &bc));
+	NB_TRY(nbgpu_dirichlet_create(K->n_cols, n, dof, value, &bc));
 	int st = nbgpu_dirichlet_apply(K, d_F, bc);
 	if (st == NBGPU_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) {
 		set_error("apply_dirichlet: %s", cudaGetErrorString(cudaGetLastError()));

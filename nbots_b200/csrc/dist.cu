@@ -25,6 +25,7 @@
 // happens at the start of K1(k+1).  Reduction messages alternate between two slots (see
 // dist_comm.cuh) and are numbered continuously across solves.
 #include "krylov_kernels.cuh"
+#include "dist_plan.cuh"
 
 using namespace nbgpu;
 
@@ -70,55 +71,47 @@ uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+namespace nbgpu {
+
+// SpMV visit order of a rank-local block: the largest (circular) run of slices that read no halo
+// column is the interior; the visit starts there, so every halo-reading slice comes last
+void plan_visit_order(nbgpu_dist_plan_s *P, const uint32_t *rows_size)
+{
+	const uint32_t off_own = P->off_own, off_up = P->off_up;
+	const uint32_t n_slices = (P->N_loc + kSliceRows - 1) / kSliceRows;
+	std::vector<uint8_t> reads_halo(n_slices, 0);
+	uint64_t k = 0;
+	for (uint32_t i = 0; i < P->N_loc; i++)
+		for (uint32_t j = 0; j < rows_size[i]; j++, k++)
+			if (P->cols_local[k] < off_own || P->cols_local[k] >= off_up)
+				reads_halo[i / kSliceRows] = 1;
+	uint32_t best_start = 0, best_len = 0;
+	bool any = false;
+	for (uint32_t s0 = 0; s0 < n_slices; s0++) {
+		if (!reads_halo[s0])
+			continue;
+		// run of clean slices that starts right after halo slice s0 (circularly)
+		any = true;
+		uint32_t len = 0;
+		while (len < n_slices && !reads_halo[(s0 + 1 + len) % n_slices])
+			len++;
+		if (len >= best_len) {
+			best_len = len;
+			best_start = (s0 + 1) % n_slices;
+		}
+	}
+	if (!any) {
+		P->visit_shift = 0;
+		P->late_from = 0xFFFFFFFFu;   // nothing to wait for
+	} else {
+		P->visit_shift = best_start;
+		P->late_from = best_len;
+	}
+}
+
+}  // namespace nbgpu
+
 // ------------------------------------------------------------------ host objects --
-
-struct nbgpu_dist_plan_s {
-	int rank = 0, world = 1;
-	std::vector<uint32_t> row_starts;      // [world + 1]
-	uint32_t N_loc = 0, n_halo = 0;
-	uint32_t n_lo = 0, n_hi = 0;           // halo columns below / above the owned range
-	uint32_t off_own = 0, off_up = 0, ext_len = 0;   // column space: [0,n_lo) | [off_own, +N_loc) | [off_up, +n_hi)
-	uint64_t nnz = 0;
-	std::vector<uint32_t> halo_global;     // [n_halo] ascending
-	std::vector<uint32_t> recv_counts;     // [world]
-	std::vector<uint32_t> cols_local;      // [nnz]
-	// sends (filled by nbgpu_dist_plan_set_sends)
-	bool have_sends = false;
-	std::vector<uint32_t> send_ptr;        // [world + 1]
-	std::vector<uint32_t> send_local;      // local row ids, grouped by destination
-	std::vector<uint32_t> dst_offset;      // [world] where my block starts in the destination's ext vector
-	uint32_t *d_send_idx = nullptr;
-	// SpMV visit order: start right after the last slice that reads halo columns, so that every
-	// halo-reading slice is visited at the end (visit index >= late_from) -- the halo wait of a
-	// kernel is then hidden behind the interior slices
-	uint32_t visit_shift = 0, late_from = 0;
-};
-
-struct nbgpu_dist_s {
-	int rank = 0, world = 1;
-	size_t ext_len = 0;                    // capacity of the two ext vectors
-	void *window = nullptr;                // control block | v_ext | x_ext
-	size_t window_bytes = 0;
-	void *peer_window[kMaxRanks] = {};
-	bool peer_is_ipc[kMaxRanks] = {};
-	bool connected = false;
-	bool broken = false;                   // an exchange failed: sequence numbers no longer agree
-	unsigned long long msg_seq = 0;        // reduction messages, numbered continuously (identical on all ranks)
-	unsigned long long halo_seq = 0;       // Krylov-vector halo pushes
-	unsigned long long spmv_seq = 0;       // input-vector halo pushes
-	KrylovState *d_state = nullptr;
-	KrylovState *h_state = nullptr;        // pinned, 4 slots + 3 error words
-	unsigned int *d_ticket = nullptr;
-	PeerTable *d_table = nullptr;          // the peer table of the plan last used, in device memory
-	const nbgpu_dist_plan_s *table_plan = nullptr;
-	cudaEvent_t poll_ev[2] = {nullptr, nullptr};
-	DistControl *ctrl() const { return (DistControl *)window; }
-	double *v_ext() const { return (double *)((char *)window + 4096); }
-	double *x_ext() const { return v_ext() + ext_len; }
-	double *peer_v_ext(int r) const { return (double *)((char *)peer_window[r] + 4096); }
-	double *peer_x_ext(int r) const { return peer_v_ext(r) + ext_len_of[r]; }
-	size_t ext_len_of[kMaxRanks] = {};
-};
 
 extern "C" {
 
@@ -198,38 +191,7 @@ int nbgpu_dist_plan_create(int rank, int world, const uint32_t *row_starts, cons
 			P->cols_local[k] = h < n_lo ? h : off_up + (h - n_lo);
 		}
 	}
-	// largest (circular) run of slices that read no halo column = the interior
-	{
-		const uint32_t n_slices = (P->N_loc + kSliceRows - 1) / kSliceRows;
-		std::vector<uint8_t> reads_halo(n_slices, 0);
-		uint64_t k = 0;
-		for (uint32_t i = 0; i < P->N_loc; i++)
-			for (uint32_t j = 0; j < rows_size[i]; j++, k++)
-				if (P->cols_local[k] < off_own || P->cols_local[k] >= off_up)
-					reads_halo[i / kSliceRows] = 1;
-		uint32_t best_start = 0, best_len = 0;
-		bool any = false;
-		for (uint32_t s0 = 0; s0 < n_slices; s0++) {
-			if (!reads_halo[s0])
-				continue;
-			// run of clean slices that starts right after halo slice s0 (circularly)
-			any = true;
-			uint32_t len = 0;
-			while (len < n_slices && !reads_halo[(s0 + 1 + len) % n_slices])
-				len++;
-			if (len >= best_len) {
-				best_len = len;
-				best_start = (s0 + 1) % n_slices;
-			}
-		}
-		if (!any) {
-			P->visit_shift = 0;
-			P->late_from = 0xFFFFFFFFu;   // nothing to wait for
-		} else {
-			P->visit_shift = best_start;
-			P->late_from = best_len;
-		}
-	}
+	plan_visit_order(P, rows_size);
 	*out = P;
 	return NBGPU_OK;
 }

@@ -206,6 +206,119 @@ class DistContext:
 
 
 # ---------------------------------------------------------------------------------------------
+class DistFem:
+    """nbgpu_dist_fem_*: this rank's piece of the static-elasticity problem on a node-range partition.
+    Assembly goes straight into the rank-local block on the device; the ranks exchange IPC handles only."""
+
+    def __init__(self, m, rank, world, node_starts, D, neu_dof, neu_add, dir_dof, dir_val, gather_obj,
+                 density=0.0, self_weight=False, gravity=(0.0, 0.0), thickness=1.0):
+        L = lib()
+        self.rank, self.world = rank, world
+        self.node_starts = np.ascontiguousarray(node_starts, dtype=np.uint32)
+        self.n0, self.n1 = int(self.node_starts[rank]), int(self.node_starts[rank + 1])
+        self.desc = capi.MeshDesc.of(m)
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        neu_dof = np.ascontiguousarray(neu_dof, dtype=np.uint32); neu_add = np.ascontiguousarray(neu_add, dtype=np.float64)
+        dir_dof = np.ascontiguousarray(dir_dof, dtype=np.uint32); dir_val = np.ascontiguousarray(dir_val, dtype=np.float64)
+        grav = (C.c_double * 2)(*gravity)
+        handle = (C.c_char * 64)()
+        h = C.c_void_p()
+        check(L.nbgpu_dist_fem_create(C.byref(self.desc), rank, world, self.node_starts.ctypes.data_as(u32p), None,
+                                      D.ctypes.data_as(f64p), density, neu_dof.size, neu_dof.ctypes.data_as(u32p),
+                                      neu_add.ctypes.data_as(f64p), dir_dof.size, dir_dof.ctypes.data_as(u32p),
+                                      dir_val.ctypes.data_as(f64p), int(self_weight), grav, thickness, handle,
+                                      C.byref(h)))
+        self.h = h.value
+        n_loc = C.c_uint32(); nnz = C.c_uint64(); n_halo = C.c_uint32(); n_el = C.c_uint32(); ext = C.c_uint64()
+        ms = C.c_double()
+        check(L.nbgpu_dist_fem_info(self.h, C.byref(n_loc), C.byref(nnz), C.byref(n_halo), C.byref(n_el), C.byref(ext),
+                                    C.byref(ms)))
+        self.N_loc, self.nnz, self.n_halo, self.n_elems, self.ext_len = n_loc.value, nnz.value, n_halo.value, \
+            n_el.value, ext.value
+        self.ms_setup = ms.value
+        everyone = gather_obj((bytes(handle), self.ext_len))
+        blob = b"".join(e[0] for e in everyone)
+        lens = np.array([e[1] for e in everyone], dtype=np.uint64)
+        check(L.nbgpu_dist_fem_connect(self.h, blob, lens.ctypes.data_as(u64p)))
+        self.A = api.Matrix(L.nbgpu_dist_fem_matrix(self.h))
+        self.A.destroy = lambda: None          # owned by the session
+        self.plan = L.nbgpu_dist_fem_plan(self.h)
+        self.dist = L.nbgpu_dist_fem_dist(self.h)
+
+        class _Raw:
+            pass
+        self.d_b = _Raw(); self.d_b.ptr = L.nbgpu_dist_fem_rhs(self.h)
+        self.d_x = _Raw(); self.d_x.ptr = L.nbgpu_dist_fem_solution(self.h)
+
+    def assemble(self, enabled=None, elem_scale=None):
+        en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
+        sc = None if elem_scale is None else np.ascontiguousarray(elem_scale, dtype=np.float64)
+        bad = C.c_uint32(0)
+        st = lib().nbgpu_dist_fem_assemble(self.h, None if en is None else en.ctypes.data_as(capi.u8p),
+                                           None if sc is None else sc.ctypes.data_as(f64p), C.byref(bad))
+        check(st, ok=(capi.OK, capi.DISTORTED_ELEMENT))
+        return st, bad.value
+
+    def solve(self, warm_start=False, max_iter=0, tol=0.0):
+        it = C.c_uint32(0); res = C.c_double(0)
+        st = lib().nbgpu_dist_fem_solve(self.h, int(warm_start), max_iter, tol, C.byref(it), C.byref(res))
+        check(st, ok=(capi.OK, capi.NOT_CONVERGED))
+        return st, it.value, res.value
+
+    def rhs(self):
+        out = np.empty(self.N_loc)
+        check(lib().nbgpu_copy_d2h(out.ctypes.data, self.d_b.ptr, out.nbytes))
+        return out
+
+    def results(self):
+        out = np.empty(self.N_loc)
+        check(lib().nbgpu_dist_fem_results(self.h, out.ctypes.data_as(f64p)))
+        return out
+
+    def rows_global(self):
+        """(rows_size, global column ids, values) of this rank's rows, for the bit-exactness checks."""
+        rs, cl = self.A.pattern_csr()
+        vals = self.A.values_csr()
+        P = PlanView(self.plan, self.world)
+        return rs, P.to_global(cl, 2 * self.n0), vals
+
+    def close(self):
+        if self.h:
+            self.A.h = None
+            lib().nbgpu_dist_fem_destroy(self.h)
+            self.h = None
+
+
+class PlanView:
+    """Read-only view of a nbgpu_dist_plan_t (layout + halo list)."""
+
+    def __init__(self, plan, world):
+        L = lib()
+        n_loc = C.c_uint32(); n_halo = C.c_uint32(); nnz = C.c_uint64()
+        self.recv_counts = np.zeros(world, dtype=np.uint32)
+        check(L.nbgpu_dist_plan_info(plan, C.byref(n_loc), C.byref(n_halo), C.byref(nnz),
+                                     self.recv_counts.ctypes.data_as(u32p)))
+        self.N_loc, self.n_halo, self.nnz = n_loc.value, n_halo.value, nnz.value
+        n_lo = C.c_uint32(); off_own = C.c_uint32(); off_up = C.c_uint32(); ext_len = C.c_uint32()
+        check(L.nbgpu_dist_plan_layout(plan, C.byref(n_lo), C.byref(off_own), C.byref(off_up), C.byref(ext_len)))
+        self.n_lo, self.off_own, self.off_up, self.ext_len = n_lo.value, off_own.value, off_up.value, ext_len.value
+        halo = np.zeros(max(1, self.n_halo), dtype=np.uint32)
+        check(L.nbgpu_dist_plan_halo_ids(plan, halo.ctypes.data_as(u32p)))
+        self.halo_global = halo[:self.n_halo]
+
+    def to_global(self, cols_local, r0):
+        cl = cols_local.astype(np.int64)
+        out = np.empty(cl.size, dtype=np.int64)
+        lo = cl < self.off_own
+        up = cl >= self.off_up
+        own = ~(lo | up)
+        out[own] = cl[own] - self.off_own + r0
+        out[lo] = self.halo_global[cl[lo]]
+        out[up] = self.halo_global[cl[up] - self.off_up + self.n_lo]
+        return out.astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------
 def bench(args, rank, world, dist):
     """bench.py body for N > 1 (torchrun, one rank per GPU): weak scaling, ~1 M dof per GPU."""
     import torch

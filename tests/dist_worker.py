@@ -168,12 +168,64 @@ def run_gpu(rank, world):
     dc.close()
 
 
+def run_gpu_fem(rank, world):
+    """nbgpu_dist_fem_*: device-side assembly of the rank-local rows (structured slabs AND the reference's
+    unstructured triangle meshes cut into contiguous node ranges), bit for bit the reference's rows; then the
+    distributed solve against the reference's run."""
+    from nbots_b200 import api, capi
+    from util import FEM_CASES, bc_records, flatten_bcs, mesh_of
+    n_dev = torch.cuda.device_count()
+    L = capi.lib()
+    capi.check(L.nbgpu_init(rank % n_dev))
+    gather = gather_obj_fn(world)
+    for name in FEM_CASES:
+        g = golden(name)
+        m = mesh_of(g)
+        neu_dof, neu_add, dir_dof, dir_val = flatten_bcs(m, bc_records(g))
+        node_starts = np.zeros(world + 1, dtype=np.uint32)
+        align = 65 if name == "quad_cantilever_64x16" else 1
+        capi.check(L.nbgpu_partition_nodes(m.n_nod, world, align, node_starts.ctypes.data_as(capi.u32p)))
+        assert node_starts[0] == 0 and node_starts[world] == m.n_nod and np.all(np.diff(node_starts.astype(np.int64)) > 0)
+        D = api.constitutive_matrix(float(g["E"]), float(g["nu"]), int(g["analysis"]))
+        fem = multigpu.DistFem(m, rank, world, node_starts, D, neu_dof, neu_add, dir_dof, dir_val, gather,
+                               density=float(g["density"]), self_weight=bool(g["self_weight"]),
+                               gravity=tuple(g["gravity"]), thickness=float(g["thickness"]))
+        en = g["enabled"] if "enabled" in g.files else None
+        st, bad = fem.assemble(enabled=en)
+        assert st == 0
+        rp = port.row_ptr_of(g["rows_size"]).astype(np.int64)
+        r0, r1 = 2 * fem.n0, 2 * fem.n1
+        rs, cols_g, vals = fem.rows_global()
+        assert np.array_equal(rs, g["rows_size"][r0:r1]), name
+        assert np.array_equal(cols_g, g["cols"][rp[r0]:rp[r1]]), name
+        assert np.array_equal(vals, g["K_post"][rp[r0]:rp[r1]]), name          # bit-exact after assembly + BCs
+        assert np.array_equal(fem.rhs(), g["F_post"][r0:r1]), name
+        assert fem.A.blocked, name
+        tol = 1e-8 * float(np.linalg.norm(g["F_post"]))
+        st, it, res = fem.solve(tol=tol)
+        ost, ox, oit, ores = port.Csr(g["rows_size"], g["cols"], g["K_post"]).pcg_jacobi(g["F_post"], tol=tol)
+        xs = gather(fem.results())
+        its = gather((st, it, res))
+        assert len(set(its)) == 1, "ranks disagree"
+        if rank == 0:
+            xg = np.concatenate(xs)
+            assert st == ost == 0 and abs(it - oit) <= max(1, int(np.ceil(0.02 * oit))), (name, it, oit)
+            assert rel_l2(xg, ox) <= (1e-9 if name == "beam_cantilever_trg1000" else 1e-10), name
+        # a second assembly + warm-started solve (the session call pattern): converged already -> few iterations
+        st, bad = fem.assemble(enabled=en)
+        st, it2, res2 = fem.solve(warm_start=True, tol=tol)
+        assert st == 0 and it2 <= max(3, it // 10), (name, it2, it)
+        fem.close()
+    if rank == 0:
+        print("DIST_OK gpu-fem")
+
+
 def main():
     mode = sys.argv[1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
     try:
-        (run_cpu if mode == "cpu" else run_gpu)(rank, world)
+        {"cpu": run_cpu, "gpu": run_gpu, "gpu-fem": run_gpu_fem}[mode](rank, world)
     finally:
         dist.destroy_process_group()
 

@@ -31,3 +31,12 @@ def test_distributed_solve_on_gpus(nbgpu_lib, world):
     within one device; the kernels of the two processes are time-sliced, so this only checks correctness)."""
     out = launch("gpu", world, 29700 + world, timeout=900, extra_env={"NBGPU_DIST_TIMEOUT_MS": "60000"})
     assert out.returncode == 0 and "DIST_OK gpu" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_fem_assembles_rank_local_rows_on_the_device(nbgpu_lib, world):
+    """nbgpu_dist_fem_*: per-rank sub-mesh assembly straight into the rank-local block (no host round trip of K),
+    bit-identical rows on all four reference fixtures (slabs and unstructured node ranges), distributed solve."""
+    out = launch("gpu-fem", world, 29800 + world, timeout=900, extra_env={"NBGPU_DIST_TIMEOUT_MS": "60000"})
+    assert out.returncode == 0 and "DIST_OK gpu-fem" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
