@@ -79,6 +79,54 @@ static double now_ms(void)
 	return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
 }
 
+/* wall-clock of the last solver call: import (nb_sparse_t -> device), solve incl. vector copies, release */
+static double g_last_ms[3];
+
+void nbshim_last_timings(double ms[3])
+{
+	ms[0] = g_last_ms[0];
+	ms[1] = g_last_ms[1];
+	ms[2] = g_last_ms[2];
+}
+
+/* Test / bench plumbing: a host nb_sparse_t with the reference's memory layout -- nb_sparse_allocate
+ * (sparse_struct.c:23-31) makes TWO heap blocks per row -- filled from flat CSR arrays. */
+nb_sparse_t *nbshim_sparse_from_csr(uint32_t N, const uint32_t *rows_size, const uint32_t *cols, const double *vals)
+{
+	nb_sparse_t *A = calloc(1, sizeof(*A));
+	if (!A)
+		return NULL;
+	A->N = N;
+	A->rows_values = calloc(N ? N : 1, sizeof(*A->rows_values));
+	A->rows_index = calloc(N ? N : 1, sizeof(*A->rows_index));
+	A->rows_size = calloc(N ? N : 1, sizeof(*A->rows_size));
+	size_t k = 0;
+	for (uint32_t i = 0; i < N; i++) {
+		const uint32_t n = rows_size[i];
+		A->rows_size[i] = n;
+		A->rows_index[i] = malloc((n ? n : 1) * sizeof(uint32_t));
+		A->rows_values[i] = malloc((n ? n : 1) * sizeof(double));
+		memcpy(A->rows_index[i], cols + k, n * sizeof(uint32_t));
+		memcpy(A->rows_values[i], vals + k, n * sizeof(double));
+		k += n;
+	}
+	return A;
+}
+
+void nbshim_sparse_free(nb_sparse_t *A)
+{
+	if (!A)
+		return;
+	for (uint32_t i = 0; i < A->N; i++) {
+		free(A->rows_index[i]);
+		free(A->rows_values[i]);
+	}
+	free(A->rows_index);
+	free(A->rows_values);
+	free(A->rows_size);
+	free(A);
+}
+
 static int solve(const nb_sparse_t *A, const double *b, double *x, uint32_t max_iter, double tolerance,
 		 uint32_t *niter_performed, double *tolerance_reached, int jacobi)
 {
@@ -94,9 +142,12 @@ static int solve(const nb_sparse_t *A, const double *b, double *x, uint32_t max_
 			    : nbgpu_cg_host(M, b, x, max_iter, tolerance, niter_performed, tolerance_reached);
 	double t2 = now_ms();
 	nbgpu_matrix_destroy(M);
+	g_last_ms[0] = t1 - t0;
+	g_last_ms[1] = t2 - t1;
+	g_last_ms[2] = now_ms() - t2;
 	if (trace)
-		fprintf(stderr, "[nbgpu shim] import %.3f ms, solve %.3f ms, release %.3f ms\n", t1 - t0, t2 - t1,
-			now_ms() - t2);
+		fprintf(stderr, "[nbgpu shim] import %.3f ms, solve %.3f ms, release %.3f ms\n", g_last_ms[0],
+			g_last_ms[1], g_last_ms[2]);
 	report(jacobi ? "nb_sparse_solve_CG_precond_Jacobi" : "nb_sparse_solve_conjugate_gradient", st);
 	LEAVE();
 	return st;

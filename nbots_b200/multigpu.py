@@ -319,8 +319,47 @@ class PlanView:
 
 
 # ---------------------------------------------------------------------------------------------
+def _checksum(a):
+    """Order-independent bit checksum of an array (64-bit words: xor and wrapping sum)."""
+    w = np.ascontiguousarray(a).view(np.uint64) if a.dtype.itemsize == 8 else np.ascontiguousarray(a).astype(np.uint64)
+    return int(np.bitwise_xor.reduce(w)) if w.size else 0, int(np.add.reduce(w, dtype=np.uint64)) if w.size else 0
+
+
+def _cantilever(nx, ny, lx, ly, rank, world, gather_obj, analysis=0, E=1.0, nu=0.3, thickness=1.0):
+    """The slab-partitioned cantilever through the C ABI (nbgpu_dist_fem_*): whole grid lines of nodes per rank."""
+    import bench as B
+    import sys
+    sys.path.insert(0, os.path.join(B.ROOT, "tests"))
+    from util import flatten_bcs
+    m = meshgen.structured_mesh(nx, ny, lx, ly, kind=1)
+    neu_dof, neu_add, dir_dof, dir_val = flatten_bcs(m, B.workload_bcs())
+    node_starts = np.zeros(world + 1, dtype=np.uint32)
+    check(lib().nbgpu_partition_nodes(m.n_nod, world, nx + 1, node_starts.ctypes.data_as(u32p)))
+    D = api.constitutive_matrix(E, nu, analysis)
+    fem = DistFem(m, rank, world, node_starts, D, neu_dof, neu_add, dir_dof, dir_val, gather_obj, thickness=thickness)
+    st, _ = fem.assemble()
+    assert st == 0
+    return m, fem, (neu_dof, neu_add, dir_dof, dir_val)
+
+
+def _single_gpu_system(m, bcs, analysis=0, E=1.0, nu=0.3, thickness=1.0):
+    """The same global system on ONE GPU through the single-GPU path (rank 0 only)."""
+    rs, cols = api.pattern_from_mesh(m)
+    K = api.Matrix.from_csr(rs, cols)
+    mesh = api.Mesh(m)
+    d_F = api.DeviceBuffer.zeros(K.N)
+    st, _ = mesh.assemble(K, d_F, E, nu, analysis=analysis, thickness=thickness)
+    assert st == 0
+    neu_dof, neu_add, dir_dof, dir_val = bcs
+    api.vector_add_entries(d_F, neu_dof, neu_add)
+    K.apply_dirichlet(d_F, dir_dof, dir_val)
+    mesh.destroy()
+    return rs, cols, K, d_F
+
+
 def bench(args, rank, world, dist):
-    """bench.py body for N > 1 (torchrun, one rank per GPU): weak scaling, ~1 M dof per GPU."""
+    """bench.py body for N > 1 (torchrun, one rank per GPU): weak scaling, ~1 M dof per GPU, through the C ABI's
+    distributed FEM path (assembly straight into the rank-local blocks on the device)."""
     import torch
     import bench as B
 
@@ -333,32 +372,43 @@ def bench(args, rank, world, dist):
         dist.all_gather_object(out, obj, group=cpu_group)
         return out
 
-    nx, ny = B.NX, B.NY_PER_GPU * world
-    t_setup = time.perf_counter()
-    prob = SlabProblem(nx, ny, 2.0, 1.0 * world, rank, world, E=B.E_MOD, nu=B.POISSON, thickness=B.THICKNESS)
-    dc = DistContext(rank, world, prob.row_starts, prob.rows_size, prob.cols_global, prob.vals, gather_obj)
-    bb = torch.tensor([float(np.dot(prob.b, prob.b))], dtype=torch.float64)
-    dist.all_reduce(bb, group=cpu_group)
-    tol = B.REL_TOL * float(np.sqrt(bb.item()))
-    N_global, N_loc = prob.N_global, prob.N_loc
-    nnz_global = sum(gather_obj(int(prob.nnz)))
-    d_b = api.DeviceBuffer.from_host(prob.b)
-    d_x = api.DeviceBuffer.zeros(N_loc)
-    t_setup = time.perf_counter() - t_setup
-
     def barrier():
         api.sync()
         dist.barrier(group=cpu_group)
+
+    def tmax(v):
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cpu_group)       # device time, max over ranks
+        return t.item()
+
+    nx, ny = B.NX, B.NY_PER_GPU * world
+    t_setup = time.perf_counter()
+    m, fem, bcs = _cantilever(nx, ny, 2.0, 1.0 * world, rank, world, gather_obj, E=B.E_MOD, nu=B.POISSON,
+                              thickness=B.THICKNESS)
+    b_loc = fem.rhs()
+    bb = torch.tensor([float(np.dot(b_loc, b_loc))], dtype=torch.float64)
+    dist.all_reduce(bb, group=cpu_group)
+    tol = B.REL_TOL * float(np.sqrt(bb.item()))
+    N_global, N_loc = 2 * m.n_nod, fem.N_loc
+    nnz_global = sum(gather_obj(int(fem.nnz)))
+    t_setup = time.perf_counter() - t_setup
+    dc = fem     # the objects the nbgpu_dist_* calls take
+
+    def dist_pcg(d_b, d_x, max_iter, tol_, A=None):
+        it = C.c_uint32(0); res = C.c_double(0)
+        st = L.nbgpu_dist_pcg_jacobi(fem.dist, fem.plan, (A or fem.A).h, d_b.ptr, d_x.ptr, max_iter, tol_,
+                                     C.byref(it), C.byref(res))
+        check(st, ok=(capi.OK, capi.NOT_CONVERGED))
+        return st, it.value, res.value
+
+    d_b, d_x = fem.d_b, fem.d_x
 
     def solve():
         check(L.nbgpu_memset(d_x.ptr, 0, N_loc * 8))
         barrier()
         api.timer_start()
-        st, it, res = dc.pcg_jacobi(d_b, d_x, N_global, tol)
-        ms = api.timer_stop()
-        t = torch.tensor([ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cpu_group)       # device time, max over ranks
-        return t.item(), st, it, res
+        st, it, res = dist_pcg(d_b, d_x, N_global, tol)
+        return tmax(api.timer_stop()), st, it, res
 
     for _ in range(args.warmup):
         solve()
@@ -376,63 +426,180 @@ def bench(args, rank, world, dist):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = float(np.mean(times))
     value = N_global * iters / (ms_step * 1e-3)
+    x_loc = fem.results()
 
     # per-kernel CUDA-event times of 256 iterations (rank 0's view)
-    check(L.nbgpu_krylov_profile(1))
-    check(L.nbgpu_memset(d_x.ptr, 0, N_loc * 8))
-    barrier()
-    dc.pcg_jacobi(d_b, d_x, 256, 0.0)
-    check(L.nbgpu_krylov_profile(0))
-    ms3 = np.zeros(3); n_prof = C.c_uint32(0)
-    check(L.nbgpu_krylov_profile_get(ms3.ctypes.data_as(f64p), C.byref(n_prof)))
-    kernel_us = [round(float(v) / max(1, n_prof.value) * 1e3, 2) for v in ms3]
-    check(L.nbgpu_memset(d_x.ptr, 0, N_loc * 8))
-    barrier()
-    dc.pcg_jacobi(d_b, d_x, N_global, tol)
+    def solve256():
+        check(L.nbgpu_memset(d_x.ptr, 0, N_loc * 8))
+        barrier()
+        dist_pcg(d_b, d_x, 256, 0.0)
+    per, _n = B.kernel_profile(L, solve256)
+    kernel_us = [round(float(v), 2) for v in per]
 
+    layout_of = (fem.A.blocked, fem.A.idx16, fem.A.uniform_width)
     # e2e: host-resident block of the matrix and host vectors on every rank, all copies timed
+    rs_loc, cols_loc = fem.A.pattern_csr()
+    vals_loc = fem.A.values_csr()
+    pv = PlanView(fem.plan, world)
     x_host = np.zeros(N_loc)
     e2e_times = []
     for k in range(1 + args.steps):
         barrier()
         t0 = time.perf_counter()
         h = C.c_void_p()
-        check(L.nbgpu_matrix_create_local(dc.N_loc, dc.ext_len, dc.off_own, dc.rows_size.ctypes.data_as(u32p),
-                                          dc.cols_local.ctypes.data_as(u32p), prob.vals.ctypes.data_as(f64p),
-                                          C.byref(h)))
+        check(L.nbgpu_matrix_create_local(N_loc, pv.ext_len, pv.off_own, rs_loc.ctypes.data_as(u32p),
+                                          cols_loc.ctypes.data_as(u32p), vals_loc.ctypes.data_as(f64p), C.byref(h)))
         A2 = api.Matrix(h.value)
-        d_b2 = api.DeviceBuffer.from_host(prob.b)
+        d_b2 = api.DeviceBuffer.from_host(b_loc)
         d_x2 = api.DeviceBuffer.from_host(x_host * 0.0)
-        A_keep, dc.A = dc.A, A2
-        st, it2, res = dc.pcg_jacobi(d_b2, d_x2, N_global, tol)
+        st, it2, res = dist_pcg(d_b2, d_x2, N_global, tol, A=A2)
         x_host = d_x2.to_host()
-        dc.A = A_keep
         dt = time.perf_counter() - t0
         A2.destroy(); d_b2.free(); d_x2.free()
-        t = torch.tensor([dt], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cpu_group)
         if k >= 1:
-            e2e_times.append(t.item())
+            e2e_times.append(tmax(dt))
     e2e_value = N_global * iters / float(np.median(e2e_times))
     # the device-resident and the host-buffer solves are the same computation
-    assert np.array_equal(x_host, d_x.to_host())
+    assert np.array_equal(x_host, x_loc)
+
+    # ---- parity: the partitioned run against the single-GPU path and the CPU reference (rank 0 judges)
+    parity = None
+    if not args.no_parity:
+        r0 = 2 * fem.n0
+        cs_local = (_checksum(rs_loc), _checksum(pv.to_global(cols_loc, r0)), _checksum(vals_loc), _checksum(b_loc))
+        check(L.nbgpu_memset(d_x.ptr, 0, N_loc * 8))
+        barrier()
+        dist_pcg(d_b, d_x, 50, 0.0)
+        x50 = gather_obj(fem.results())
+        everyone = gather_obj((cs_local, fem.n0, fem.n1))
+        if rank == 0:
+            rs, cols, K1, d_F1 = _single_gpu_system(m, bcs, E=B.E_MOD, nu=B.POISSON, thickness=B.THICKNESS)
+            vals1 = K1.values_csr(); b1 = d_F1.to_host()
+            rp = np.zeros(rs.size + 1, dtype=np.int64); np.cumsum(rs, out=rp[1:])
+            rows_ok = True
+            for cs, a, e in everyone:
+                lo, hi = 2 * a, 2 * e
+                ref_cs = (_checksum(rs[lo:hi]), _checksum(cols[rp[lo]:rp[hi]]), _checksum(vals1[rp[lo]:rp[hi]]),
+                          _checksum(b1[lo:hi]))
+                rows_ok = rows_ok and (cs == ref_cs)
+            d_x1 = api.DeviceBuffer.zeros(K1.N)
+            K1.pcg_jacobi(d_F1, d_x1, max_iter=50, tol=0.0)
+            x50_single = d_x1.to_host()
+            x50_dist = np.concatenate(x50)
+            rel_single = float(np.linalg.norm(x50_dist - x50_single) / np.linalg.norm(x50_single))
+            check(L.nbgpu_memset(d_x1.ptr, 0, K1.N * 8))
+            st1, it1, res1 = K1.pcg_jacobi(d_F1, d_x1, max_iter=K1.N, tol=tol)
+            kind, Kref, Fref = B.reference_system(m)
+            stc, xc, itc, resc = Kref.pcg_jacobi(Fref, max_iter=50, tol=0.0, threads=os.cpu_count() or 1)
+            rel_cpu = float(np.linalg.norm(x50_dist - xc) / np.linalg.norm(xc))
+            vals_ref = Kref.export()[2] if kind == "reference" else Kref.vals
+            parity = {"rows_bit_identical_to_single_gpu": bool(rows_ok),
+                      "K_bit_identical_to_cpu_reference": bool(np.array_equal(vals_ref, vals1)),
+                      "F_bit_identical_to_cpu_reference": bool(np.array_equal(Fref, b1)),
+                      "x50_rel_l2_vs_single_gpu": rel_single, "x50_rel_l2_vs_cpu_reference": rel_cpu,
+                      "cpu_reference_kind": kind,
+                      "iterations": int(iters), "iterations_single_gpu": int(it1),
+                      "iterations_within_2pct": bool(abs(iters - it1) <= max(1, int(np.ceil(0.02 * it1))))}
+            parity["ok"] = bool(rows_ok and parity["K_bit_identical_to_cpu_reference"]
+                                and parity["F_bit_identical_to_cpu_reference"] and rel_single <= 1e-12
+                                and rel_cpu <= 1e-12 and parity["iterations_within_2pct"])
+            K1.destroy(); d_F1.free(); d_x1.free()
+            del rs, cols, vals1, Kref
+        barrier()
+    fem.close()
+    del m
+
+    # ---- target: Q16 split into `world` slabs (strong scaling), fixed iteration budget
+    target = None
+    if not args.no_target:
+        nx16, ny16 = B.Q16
+        t0 = time.perf_counter()
+        m16, f16, bcs16 = _cantilever(nx16, ny16, 2.0, 1.0, rank, world, gather_obj, analysis=1, E=B.E_MOD,
+                                      nu=B.POISSON, thickness=B.THICKNESS)
+        setup16 = time.perf_counter() - t0
+        N16 = 2 * m16.n_nod
+        nnz16 = sum(gather_obj(int(f16.nnz)))
+        best = 1e30
+        for rep in range(2):
+            check(L.nbgpu_memset(f16.d_x.ptr, 0, f16.N_loc * 8))
+            barrier()
+            api.timer_start()
+            it = C.c_uint32(0); res = C.c_double(0)
+            st = L.nbgpu_dist_pcg_jacobi(f16.dist, f16.plan, f16.A.h, f16.d_b.ptr, f16.d_x.ptr, B.TARGET_ITERS, 0.0,
+                                         C.byref(it), C.byref(res))
+            check(st, ok=(capi.OK, capi.NOT_CONVERGED))
+            best = min(best, tmax(api.timer_stop()))
+
+        def solve256_16():
+            check(L.nbgpu_memset(f16.d_x.ptr, 0, f16.N_loc * 8))
+            barrier()
+            it_ = C.c_uint32(0); res_ = C.c_double(0)
+            L.nbgpu_dist_pcg_jacobi(f16.dist, f16.plan, f16.A.h, f16.d_b.ptr, f16.d_x.ptr, 256, 0.0, C.byref(it_),
+                                    C.byref(res_))
+        x16 = gather_obj(f16.results())      # the iterate after the fixed budget
+        per16, _n = B.kernel_profile(L, solve256_16)
+        layout16 = {"blocked": f16.A.blocked, "idx16": f16.A.idx16, "uniform_width": f16.A.uniform_width}
+        phys_k1 = B.matrix_bytes_moved(f16.A) + 16 * f16.N_loc
+        alg_k1 = 12 * f16.nnz + 20 * f16.N_loc + 4
+        n_halo16 = f16.n_halo
+        f16.close()
+        us_it = best * 1e3 / B.TARGET_ITERS
+        peak, _src = B.measured_peaks()
+        single = None
+        if rank == 0:
+            # one GPU, same run: the strong-scaling denominator (and a check of the partitioned iterates)
+            rs, cols, K1, d_F1 = _single_gpu_system(m16, bcs16, analysis=1, E=B.E_MOD, nu=B.POISSON, thickness=B.THICKNESS)
+            del cols
+            d_x1 = api.DeviceBuffer.zeros(K1.N)
+            b1 = 1e30
+            for rep in range(2):
+                check(L.nbgpu_memset(d_x1.ptr, 0, K1.N * 8))
+                api.timer_start()
+                K1.pcg_jacobi(d_F1, d_x1, max_iter=B.TARGET_ITERS, tol=0.0)
+                b1 = min(b1, api.timer_stop())
+            x1 = d_x1.to_host()
+            xd = np.concatenate(x16)
+            single = {"us_per_iteration": round(b1 * 1e3 / B.TARGET_ITERS, 2),
+                      "x_rel_l2_partitioned_vs_single_gpu_after_budget": float(np.linalg.norm(xd - x1) / np.linalg.norm(x1))}
+            K1.destroy(); d_F1.free(); d_x1.free()
+            target = {"n_gpus": world,
+                      "q16": {"workload": f"Q16: structured-quad cantilever {nx16}x{ny16}, 'plane strain' flag (reference "
+                                          f"semantics: plane-stress D), {world} slabs of grid lines assembled on the "
+                                          "devices (nbgpu_dist_fem_*), Jacobi-PCG, fixed budget from x0 = 0 "
+                                          "(BASELINE.json configs[3])",
+                              "N_dof": int(N16), "nnz": int(nnz16), "iterations": B.TARGET_ITERS,
+                              "us_per_iteration": round(us_it, 2), "dof_iter_per_s": N16 * B.TARGET_ITERS / (best * 1e-3),
+                              "kernel_us_rank0": [round(float(v), 2) for v in per16],
+                              "k1_GBps_algorithmic_per_gpu": round(alg_k1 / (per16[0] * 1e-6) / 1e9, 1),
+                              "k1_GBps_physical_per_gpu": round(phys_k1 / (per16[0] * 1e-6) / 1e9, 1),
+                              "k1_frac_of_peak_physical": round(phys_k1 / (per16[0] * 1e-6) / 1e9 / peak, 4),
+                              "iteration_GBps_algorithmic_per_gpu": round((12 * nnz16 + 108 * N16) / (us_it * 1e-6) / 1e9 / world, 1),
+                              "halo_values_per_rank": int(n_halo16), "local_block_layout": layout16,
+                              "single_gpu_same_run": single,
+                              "strong_scaling_efficiency": round(single["us_per_iteration"] / (world * us_it), 4),
+                              "setup_s": round(setup16, 2)}}
+        barrier()
 
     peak, peak_src = B.measured_peaks()
     bytes_iter = 12 * nnz_global + 108 * N_global
+    rc = 0
     if rank == 0:
         line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": B.workload_name(world),
                            "N_dof": int(N_global), "nnz": int(nnz_global), "iterations_per_step": int(iters),
-                           "rel_tol": B.REL_TOL, "dof_per_gpu": int(N_loc), "halo_values_per_rank": int(dc.n_halo),
+                           "rel_tol": B.REL_TOL, "dof_per_gpu": int(N_loc), "halo_values_per_rank": int(pv.n_halo),
                            "exchange": "NVLink peer stores + sequence flags (CUDA IPC windows); no NCCL in the loop",
+                           "assembly": "per-rank sub-mesh straight into the rank-local block on the device "
+                                       "(nbgpu_dist_fem_*); K never visits the host",
+                           "pcg_mode": os.environ.get("NBGPU_PCG_MODE", "classic (default)"),
                            "l2": "per-GPU working set 265 MB exceeds the 126 MB L2; no flush",
-                           "local_block_layout": {"blocked": dc.A.blocked, "idx16": dc.A.idx16,
-                                                  "uniform_width": dc.A.uniform_width},
+                           "local_block_layout": {"blocked": bool(layout_of[0]),
+                                                  "idx16": bool(layout_of[1]), "uniform_width": int(layout_of[2])},
                            "kernel_us_rank0": kernel_us, "us_per_iteration": round(ms_step * 1e3 / iters, 2),
                            "setup_s": round(t_setup, 2)},
-                "roofline": {"bound": "hbm", "kernel": "whole iteration (dist_spmv + dist_update + dist_dir + halo_push)",
+                "roofline": {"bound": "hbm", "kernel": "whole iteration (K1 SpMV+dot with halo push, K2, K3)",
                              "achieved": round(bytes_iter * iters / (ms_step * 1e-3) / 1e9 / world, 1),
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s per GPU",
                              "frac": round(bytes_iter * iters / (ms_step * 1e-3) / 1e9 / world / peak, 4),
@@ -443,8 +610,13 @@ def bench(args, rank, world, dist):
                         "d2h_bytes_per_step": int(8 * N_global),
                         "ms_per_step": round(float(np.median(e2e_times)) * 1e3, 2),
                         "entry_point": "nbgpu_matrix_create_local + nbgpu_dist_pcg_jacobi, host buffers per rank"},
+                "parity": parity, "target": target,
                 "gpu_launches": int(launches) * world, "clocks": clocks}
-        print(json.dumps(line))
-    dc.close()
+        print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            print("bench: PARITY FAILED " + json.dumps(parity), file=sys.stderr, flush=True)
+            rc = 1
     dist.barrier(group=cpu_group)
     dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
