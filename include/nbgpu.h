@@ -550,6 +550,36 @@ nbgpu_dist_t *nbgpu_dist_fem_dist(nbgpu_dist_fem_t *fem);
 double *nbgpu_dist_fem_rhs(nbgpu_dist_fem_t *fem);        /* device, N_loc */
 double *nbgpu_dist_fem_solution(nbgpu_dist_fem_t *fem);   /* device, N_loc */
 
+/* ------------------------- several GPUs from one (single-threaded) caller -- */
+/* The reference's callers are ordinary single-process programs.  These entry
+ * points keep that shape: the call blocks, inside it one worker thread per GPU
+ * runs the rank code above with peer access between the windows.  The
+ * reference-named shims use them when NBGPU_DEVICES=N (N > 1) is set. */
+int nbgpu_devices_from_env(void);
+/* nb_fem_compute_2D_Solid_Mechanics (static_elasticity2D.c:31-97) on n_devices
+ * GPUs; arguments as nbgpu_fem_static_elasticity2d_lists (row-parallel assembly) */
+int nbgpu_fem_static_elasticity2d_lists_multi(int n_devices,
+					      const nbgpu_mesh_desc_t *mesh,
+					      const nbgpu_elem_tables_t *tables,
+					      const double D[4], double density,
+					      uint32_t n_neumann,
+					      const uint32_t *neumann_dof,
+					      const double *neumann_add,
+					      uint32_t n_dirichlet,
+					      const uint32_t *dirichlet_dof,
+					      const double *dirichlet_val,
+					      int self_weight, const double gravity[2],
+					      double thickness, const uint8_t *enabled,
+					      double solver_tol, double *displacement,
+					      double *strain, nbgpu_fem_report_t *report);
+/* nb_sparse_solve_CG_precond_Jacobi (jacobi != 0) / nb_sparse_solve_conjugate_gradient
+ * on the three arrays of a host nb_sparse_t, contiguous row blocks over n_devices GPUs */
+int nbgpu_solve_rows_multi(int n_devices, int jacobi, uint32_t N,
+			   const uint32_t *rows_size, uint32_t *const *rows_index,
+			   double *const *rows_values, const double *b, double *x,
+			   uint32_t max_iter, double tolerance,
+			   uint32_t *niter_performed, double *tolerance_reached);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,6 +146,12 @@ SIGNATURES = {
                                 u32p, f64p]),
     "nbgpu_dist_input_vector": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "nbgpu_dist_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nbgpu_devices_from_env": (C.c_int, []),
+    "nbgpu_fem_static_elasticity2d_lists_multi": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, f64p, C.c_double, C.c_uint32,
+                                                            u32p, f64p, C.c_uint32, u32p, f64p, C.c_int, f64p,
+                                                            C.c_double, u8p, C.c_double, f64p, f64p, C.c_void_p]),
+    "nbgpu_solve_rows_multi": (C.c_int, [C.c_int, C.c_int, C.c_uint32, u32p, C.c_void_p, C.c_void_p, f64p, f64p,
+                                         C.c_uint32, C.c_double, u32p, f64p]),
     "nbgpu_partition_nodes": (C.c_int, [C.c_uint32, C.c_int, C.c_uint32, u32p]),
     "nbgpu_dist_fem_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, C.c_void_p, f64p, C.c_double, C.c_uint32,
                                         u32p, f64p, C.c_uint32, u32p, f64p, C.c_int, f64p, C.c_double, C.c_void_p,

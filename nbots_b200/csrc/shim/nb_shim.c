@@ -79,6 +79,13 @@ static double now_ms(void)
 	return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
 }
 
+/* systems smaller than this stay on one GPU even when NBGPU_DEVICES asks for more (NBGPU_MULTI_MIN_ROWS) */
+static uint32_t multi_min_rows(void)
+{
+	const char *env = getenv("NBGPU_MULTI_MIN_ROWS");
+	return env ? (uint32_t)strtoul(env, NULL, 10) : 200000u;
+}
+
 /* wall-clock of the last solver call: import (nb_sparse_t -> device), solve incl. vector copies, release */
 static double g_last_ms[3];
 
@@ -134,6 +141,18 @@ static int solve(const nb_sparse_t *A, const double *b, double *x, uint32_t max_
 	const int trace = getenv("NBGPU_TRACE") != NULL;
 	ENTER();
 	double t0 = now_ms();
+	const int n_dev = nbgpu_devices_from_env();
+	if (n_dev > 1 && A->N >= multi_min_rows()) {
+		/* NBGPU_DEVICES=N: contiguous row blocks over N GPUs, one worker thread per GPU */
+		int mst = nbgpu_solve_rows_multi(n_dev, jacobi, A->N, A->rows_size, A->rows_index, A->rows_values, b, x,
+						 max_iter, tolerance, niter_performed, tolerance_reached);
+		g_last_ms[0] = 0;
+		g_last_ms[1] = now_ms() - t0;
+		g_last_ms[2] = 0;
+		report(jacobi ? "nb_sparse_solve_CG_precond_Jacobi" : "nb_sparse_solve_conjugate_gradient", mst);
+		LEAVE();
+		return mst;
+	}
 	int st = nbgpu_matrix_create_from_rows(A->N, A->rows_size, A->rows_index, A->rows_values, &M);
 	double t1 = now_ms();
 	if (st == NBGPU_OK)
@@ -591,11 +610,19 @@ int nb_fem_compute_2D_Solid_Mechanics(const nb_mesh2D_t *const part, const nb_fe
 		double D[4];
 		R.constitutive(D, material, analysis2D);
 		ENTER();
-		st = nbgpu_fem_static_elasticity2d_lists(&fm.d, &tab, D, R.mat_density(material), neu.n,
-							 neu.dof, neu.val, dir.n, dir.dof, dir.val,
-							 enable_self_weight, gravity, analysis2D,
-							 params2D->thickness, (const uint8_t *)elements_enabled,
-							 NBGPU_ASSEMBLY_GATHER, 0.0, displacement, strain, NULL);
+		const int n_dev = nbgpu_devices_from_env();
+		if (n_dev > 1 && 2 * fm.d.N_nod >= multi_min_rows())
+			st = nbgpu_fem_static_elasticity2d_lists_multi(n_dev, &fm.d, &tab, D, R.mat_density(material), neu.n,
+								       neu.dof, neu.val, dir.n, dir.dof, dir.val,
+								       enable_self_weight, gravity, params2D->thickness,
+								       (const uint8_t *)elements_enabled, 0.0, displacement,
+								       strain, NULL);
+		else
+			st = nbgpu_fem_static_elasticity2d_lists(&fm.d, &tab, D, R.mat_density(material), neu.n,
+								 neu.dof, neu.val, dir.n, dir.dof, dir.val,
+								 enable_self_weight, gravity, analysis2D,
+								 params2D->thickness, (const uint8_t *)elements_enabled,
+								 NBGPU_ASSEMBLY_GATHER, 0.0, displacement, strain, NULL);
 		LEAVE();
 	}
 	free(neu.dof); free(neu.val); free(dir.dof); free(dir.val);

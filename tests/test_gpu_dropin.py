@@ -78,6 +78,18 @@ def test_reference_call_sites_run_on_the_device(nbgpu_lib):
     assert out.returncode == 0 and "DROPIN_OK" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnbots_ref.so not present")
+def test_reference_call_sites_run_on_two_devices(nbgpu_lib):
+    """The same interposition run with NBGPU_DEVICES=2: the reference's single-threaded callers (its FEM driver,
+    its solver entry on a genuine nb_sparse_t) are served by two GPUs of the box -- one worker thread per GPU
+    inside the shim, peer access between the windows -- and must produce the same results."""
+    if nbgpu_lib.nbgpu_device_count() < 2:
+        pytest.skip("needs two GPUs in the box")
+    env = dict(os.environ, NBGPU_DEVICES="2", NBGPU_MULTI_MIN_ROWS="0", NBGPU_DIST_TIMEOUT_MS="60000")
+    out = subprocess.run([sys.executable, "-c", SCRIPT % ROOT], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and "DROPIN_OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_shim_entry_points_tolerate_concurrent_callers(nbgpu_lib):
     """The reference's solver entry points are re-entrant; the shim serialises callers that arrive from
     several host threads (one device context per process) instead of corrupting its work vectors."""
@@ -102,8 +114,8 @@ def test_shim_entry_points_tolerate_concurrent_callers(nbgpu_lib):
     for name in ("quad_cantilever_64x16", "plate_with_hole_trg1000", "quad_void_selfweight_24x8"):
         g = golden(name)
         rs, cols, vals = g["rows_size"].copy(), g["cols"].copy(), g["K_post"].copy()
-        A, keep = bench.host_nb_sparse(rs, cols, vals)
-        cases.append((g, A, keep, rs, cols, vals))
+        A = bench.host_nb_sparse(shim, rs, cols, vals)      # the reference's layout: two heap blocks per row
+        cases.append((g, A, None, rs, cols, vals))
     errors = []
 
     def worker(idx):
@@ -115,10 +127,10 @@ def test_shim_entry_points_tolerate_concurrent_callers(nbgpu_lib):
                 x = np.zeros(rs.size)
                 it = C.c_uint32(0)
                 res = C.c_double(0)
-                st = pcg(C.byref(A), b.ctypes.data_as(capi.f64p), x.ctypes.data_as(capi.f64p), rs.size, tol,
+                st = pcg(A, b.ctypes.data_as(capi.f64p), x.ctypes.data_as(capi.f64p), rs.size, tol,
                          C.byref(it), C.byref(res), 1)
                 y = np.zeros(rs.size)
-                mv(C.byref(A), x.ctypes.data_as(capi.f64p), y.ctypes.data_as(capi.f64p), 1)
+                mv(A, x.ctypes.data_as(capi.f64p), y.ctypes.data_as(capi.f64p), 1)
                 if st != 0 or np.linalg.norm(y - b) > 2 * tol:
                     errors.append((idx, st, float(np.linalg.norm(y - b)), tol))
         except Exception as e:                       # pragma: no cover
