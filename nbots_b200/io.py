@@ -192,3 +192,55 @@ def load_vtk(path) -> Mesh2D:
     return Mesh2D(kind=kind, nod=pts[:, :2].ravel().copy(), edg=sides.ravel().copy(), adj=adj.ravel().copy(),
                   vtx=np.zeros(0, np.uint32), sgm_sizes=np.zeros(0, np.uint32), sgm_nodes=np.zeros(0, np.uint32),
                   nx=0, ny=0)
+
+
+# ---- NBT (mesh2D/file_format_nbt.c) ---------------------------------------------------------------------------
+# What the reference implements of this format for the FEM path's two mesh kinds is the HEADER: its triangle and
+# quad data writers are empty and their readers return 1 (elements2D/msh3trg_file_format_nbt.c:9-17,
+# mshquad_file_format_nbt.c:13-22); only polygon meshes carry data.  Mirrored as it is: save_nbt writes the
+# byte-identical header, read_nbt_type parses it (nb_mesh2D_read_type_nbt, file_format_nbt.c:99-160), and
+# load_nbt fails the way nb_mesh2D_read_nbt does -- a mesh has to travel as VTK (above) or as arrays.
+NBT_HEADER = "[Numerical Bots File Format v1.0]"          # headers/nb/io_bot/nbt_file_format.h:4
+_NBT_TYPES = {0: "NB_TRIAN", 1: "NB_QUAD"}
+
+
+def save_nbt(path, m: Mesh2D) -> int:
+    """nb_mesh2D_save_nbt (file_format_nbt.c:28-45): 0 on success, 1 if the file cannot be opened."""
+    try:
+        with open(path, "w") as fp:
+            fp.write("%s\nClass = mesh2D\nType = %s\n\n" % (NBT_HEADER, _NBT_TYPES[m.kind]))
+    except OSError:
+        return 1
+    return 0
+
+
+def read_nbt_type(path):
+    """nb_mesh2D_read_type_nbt -> (status, kind): 0 and 0 / 1 (triangles / quads) for a mesh2D NBT file of one of the
+    two FEM mesh kinds, status 1 otherwise (missing file, wrong header or class, another type)."""
+    try:
+        with open(path) as fp:
+            lines = [ln.split("#")[0].strip() for ln in fp]
+    except OSError:
+        return 1, None
+    lines = [ln for ln in lines if ln]
+    if len(lines) < 3 or lines[0] != NBT_HEADER:
+        return 1, None
+    var, _, val = lines[1].partition("=")
+    if var.strip() != "Class" or val.strip() != "mesh2D":
+        return 1, None
+    var, _, val = lines[2].partition("=")
+    if var.strip() != "Type":
+        return 1, None
+    for kind, name in _NBT_TYPES.items():
+        if val.strip() == name:
+            return 0, kind
+    return 1, None
+
+
+def load_nbt(path, kind) -> int:
+    """nb_mesh2D_read_nbt for a triangle / quad mesh: status 1 -- after the header and type checks the reference
+    calls a data reader that is not implemented for these kinds and reports failure (file_format_nbt.c:163-191)."""
+    st, _found = read_nbt_type(path)
+    if st != 0 or _found != kind:
+        return 1
+    return 1

@@ -1,5 +1,5 @@
 """Writes tests/golden/io/*: small files produced by the REFERENCE's own writers (nb_sparse_save,
-nb_sparse_save_mat4, nb_mat4_save_vec, nb_mesh2D_save_vtk), for tests/test_io.py.  Needs oracle/_ref.
+nb_sparse_save_mat4, nb_mat4_save_vec, nb_mesh2D_save_vtk, nb_mesh2D_save_nbt), for tests/test_io.py.  Needs oracle/_ref.
 TEST INFRASTRUCTURE, not product code."""
 import os
 import sys
@@ -30,4 +30,5 @@ for kind in (0, 1):
     rm = ref.RefMesh.from_arrays(m)
     name = "grid_%s.vtk" % ("quad" if kind else "trg")
     assert L.refh_mesh_save_vtk(rm.h, name.encode()) == 0
+    assert L.refh_mesh_save_nbt(rm.h, name.replace(".vtk", ".nbt").encode()) == 0
 print(sorted((f, os.path.getsize(f)) for f in os.listdir(".")))

@@ -88,6 +88,15 @@ def lib():
         L.refh_main_stress.argtypes = [C.c_uint32, f64p, f64p]
         L.refh_stress_from_strain.argtypes = [C.c_uint32, C.c_int, C.c_double, C.c_double, C.c_int, f64p,
                                               u8p, f64p]
+        L.refh_mesh_save_nbt.restype = C.c_int
+        L.refh_mesh_save_nbt.argtypes = [C.c_void_p, C.c_char_p]
+        L.refh_mesh_read_type_nbt.restype = C.c_int
+        L.refh_mesh_read_type_nbt.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+        L.refh_mesh_read_nbt.restype = C.c_int
+        L.refh_mesh_read_nbt.argtypes = [C.c_void_p, C.c_char_p]
+        L.refh_inv_power.restype = C.c_int
+        L.refh_inv_power.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, f64p, f64p, C.POINTER(C.c_int),
+                                     C.c_double, C.c_uint32]
         _lib = L
     return _lib
 
@@ -317,3 +326,10 @@ def stress_from_strain(n_elems, elem_type, E, nu, analysis, strain, enabled=None
     lib().refh_stress_from_strain(n_elems, elem_type, E, nu, analysis, _p(strain, f64p), _p(en, u8p),
                                   _p(stress, f64p))
     return stress
+
+
+def inv_power(A: "RefSparse", h, mu=0.0, tolerance=1e-8, use_jacobi=True, threads=1):
+    """nb_sparse_eigen_ipower (eigen/inv_power.c:13-130) with the Krylov solvers inside -> (status, vecs[h][N], vals, its)."""
+    vecs = np.zeros((h, A.N)); vals = np.zeros(h); its = (C.c_int * h)()
+    st = lib().refh_inv_power(A.h, int(use_jacobi), h, float(mu), _p(vecs, f64p), _p(vals, f64p), its, tolerance, threads)
+    return st, vecs, vals, list(its)

@@ -352,6 +352,25 @@ int refh_cg(const void *A, const double *b, double *x,
 						  iters, tol_reached, threads);
 }
 
+/* the reference's OTHER caller of the two Krylov entry points that can be run as it is:
+ * inverse power iteration (eigen/inv_power.c:75 Jacobi-PCG, :80 plain CG).  The model regulariser
+ * (geometric_bot/model/modules2D/regularizer.c:24-57) cannot: nb_model_load_vtx_graph (model2D.c:276,288)
+ * hands the container ARRAY to nb_container_init / _finish instead of its i-th element and crashes before
+ * the solver is reached; tests/test_gpu_dropin.py restates its system (regularizer.c:74-108) instead. */
+int refh_inv_power(const void *A, int use_jacobi, int h, double mu, double *eigenvecs /* [h][N] */,
+		   double *eigenvals, int *it, double tolerance, uint32_t threads)
+{
+	const uint32_t N = ((const nb_sparse_t *)A)->N;
+	double **vecs = malloc((size_t)h * sizeof(*vecs));
+	for (int i = 0; i < h; i++)
+		vecs[i] = eigenvecs + (size_t)i * N;
+	/* any value other than the two direct solvers and CGJ selects plain CG (inv_power.c:79-83) */
+	int st = nb_sparse_eigen_ipower(A, use_jacobi ? NB_SOLVER_CGJ : (nb_solver_t)99, h, mu, vecs, eigenvals,
+					it, tolerance, threads);
+	free(vecs);
+	return st;
+}
+
 void refh_dirichlet(void *A, double *rhs, uint32_t idx, double value)
 {
 	nb_sparse_set_Dirichlet_condition(A, rhs, idx, value);
@@ -549,6 +568,23 @@ void refh_stress_from_strain(uint32_t N_elems, int elem_type, double E,
 	free(en);
 	nb_material_destroy(mat);
 	nb_fem_elem_destroy(e);
+}
+
+/* NBT mesh file format (mesh2D/file_format_nbt.c), called as it is */
+int refh_mesh_save_nbt(const void *hp, const char *path)
+{
+	return nb_mesh2D_save_nbt(((const refh_mesh_t *)hp)->mesh, path);
+}
+int refh_mesh_read_type_nbt(const char *path, int *type)
+{
+	nb_mesh2D_type t = NB_TRIAN;
+	int st = nb_mesh2D_read_type_nbt(path, &t);
+	*type = (int)t;
+	return st;
+}
+int refh_mesh_read_nbt(void *hp, const char *path)
+{
+	return nb_mesh2D_read_nbt(((refh_mesh_t *)hp)->mesh, path);
 }
 
 /* the reference mesh pointer itself, for the drop-in shim tests */

@@ -64,6 +64,12 @@ SCRIPT = textwrap.dedent('''
         # (4) post-processing entry: Gauss points -> nodes through the shim, on the reference's mesh object
         st, nodal = ref.gp_to_nodes(rm, kind, m.n_nod, 3, g["stress"])
         assert st == 0 and np.array_equal(nodal, g["stress_nod"]), name
+        # (5) nb_fem_compute_stress_from_strain through the shim (static_elasticity2D.c:99-127)
+        assert C.cast(shim.nb_fem_compute_stress_from_strain, C.c_void_p).value != \
+            C.cast(L.nb_fem_compute_stress_from_strain, C.c_void_p).value
+        stress = ref.stress_from_strain(m.n_elems, kind, float(g["E"]), float(g["nu"]), int(g["analysis"]),
+                                        g["strain"], enabled=en)
+        assert np.array_equal(stress, g["stress"]), name
         if name.startswith("beam"):
             assert abs(np.sqrt((disp.reshape(-1, 2) ** 2).sum(axis=1)).max() - 1.00701e-1) < 1e-6
     launched = capi.lib().nbgpu_launch_count() - before
@@ -88,6 +94,99 @@ def test_reference_call_sites_run_on_two_devices(nbgpu_lib):
     env = dict(os.environ, NBGPU_DEVICES="2", NBGPU_MULTI_MIN_ROWS="0", NBGPU_DIST_TIMEOUT_MS="60000")
     out = subprocess.run([sys.executable, "-c", SCRIPT % ROOT], capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0 and "DROPIN_OK" in out.stdout, out.stdout + out.stderr
+
+
+OTHER_CALLERS = textwrap.dedent('''
+    import ctypes as C, json, os, sys
+    import numpy as np
+    ROOT = %r
+    WITH_SHIM = %d
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if WITH_SHIM:
+        from nbots_b200 import capi
+        C.CDLL(capi.LIB_PATH, mode=C.RTLD_GLOBAL)
+        shim = C.CDLL(capi.SHIM_PATH, mode=C.RTLD_GLOBAL)        # in front of the reference
+        capi.check(capi.lib().nbgpu_set_reduction_order(WITH_SHIM - 1))   # 1: parallel tree, 2: reference order
+    from oracle import ref
+    from util import golden
+    from nbots_b200 import meshgen
+    C.CDLL(ref.LIB_PATH, mode=C.RTLD_GLOBAL)
+    out = {}
+    # (a) inverse power iteration (eigen/inv_power.c:55-105): Jacobi-PCG (:75) and plain CG (:80) inside
+    g = golden("lap9_48")
+    n_adj, adj = meshgen.laplacian9_graph(48)
+    A = ref.RefSparse.from_graph(n_adj, adj, 1)
+    A.set_values(g["vals"])
+    for name, jac in (("ipower_cgj", True), ("ipower_cg", False)):
+        st, vecs, vals, its = ref.inv_power(A, 3, mu=0.0, tolerance=1e-6, use_jacobi=jac)
+        out[name] = {"status": st, "vals": vals.tolist(), "its": its, "vecs": vecs.ravel().tolist()}
+    # (b) the model regulariser's solve (modules2D/regularizer.c:24-57): a jagged closed polygon, four vertices
+    # pinned.  nb_model_regularize itself crashes in the reference (nb_model_load_vtx_graph, model2D.c:276 hands
+    # the container array to nb_container_init), so its system is restated here -- matrix from the reference's
+    # nb_sparse_create on the vertex graph, entries as regularizer.c:74-108, pinned vertices through the
+    # reference's nb_sparse_set_Dirichlet_condition -- and solved with ITS call: x0 = the current vertices,
+    # max_iter = N, absolute tolerance 1e-12 (regularizer.c:49).
+    rng = np.random.default_rng(7)
+    nv, lam = 400, 0.5
+    t = np.linspace(0, 2 * np.pi, nv, endpoint=False)
+    r = 1.0 + 0.05 * rng.standard_normal(nv)
+    vertex = np.stack([r * np.cos(t), r * np.sin(t)], axis=1).ravel()
+    nxt, prv = (np.arange(nv) + 1) %% nv, (np.arange(nv) - 1) %% nv
+    n_adj = np.full(nv, 2, dtype=np.uint32)
+    adj = np.sort(np.stack([prv, nxt], axis=1), axis=1).astype(np.uint32).ravel()
+    K = ref.RefSparse.from_graph(n_adj, adj, 2)
+    rs, cols, _ = K.export()
+    rp = np.zeros(rs.size + 1, dtype=np.int64); np.cumsum(rs, out=rp[1:])
+    vals = np.zeros(cols.size); b = np.zeros(2 * nv)
+    def add(i, j, v):
+        k = rp[i] + int(np.searchsorted(cols[rp[i]:rp[i + 1]], j)); assert cols[k] == j; vals[k] += v
+    for e in range(nv):                                     # edge e = (e, e + 1)
+        vi, vj = e, int(nxt[e])
+        for a in (0, 1):
+            add(2 * vi + a, 2 * vi + a, 1.0); add(2 * vi + a, 2 * vj + a, -lam)
+            add(2 * vj + a, 2 * vi + a, -lam); add(2 * vj + a, 2 * vj + a, 1.0)
+            b[2 * vi + a] += (1.0 - lam) * vertex[2 * vi + a]
+            b[2 * vj + a] += (1.0 - lam) * vertex[2 * vj + a]
+    K.set_values(vals)
+    for fv in (0, 100, 200, 300):
+        for a in (0, 1):
+            K.dirichlet(b, 2 * fv + a, vertex[2 * fv + a])
+    st, v, it, res = K.pcg_jacobi(b, x0=vertex, max_iter=2 * nv, tol=1e-12)
+    out["regularize"] = {"status": st, "vertex": v.tolist(), "iters": it}
+    if WITH_SHIM:
+        out["launches"] = int(capi.lib().nbgpu_launch_count())
+    print("RESULT " + json.dumps(out))
+''')
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnbots_ref.so not present")
+def test_other_krylov_callers_of_the_reference_through_the_shim(nbgpu_lib):
+    """SURVEY.md §8 f4: the reference's other users of the two solver entry points -- inverse power iteration
+    (inv_power.c:75 Jacobi-PCG, :80 plain CG), run unmodified, and the model regulariser's solve (regularizer.c:49;
+    its system restated, see the script) -- with libnbots_b200.so interposed; results against the same calls on the CPU: bit-identical with reference-order
+    dot products, within solver tolerance with the default parallel-tree reductions."""
+    import json
+
+    import numpy as np
+
+    def run(with_shim):
+        out = subprocess.run([sys.executable, "-c", OTHER_CALLERS % (ROOT, with_shim)], capture_output=True, text=True,
+                             timeout=900)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
+
+    cpu, tree, exact = run(0), run(1), run(2)
+    assert tree["launches"] > 1000 and exact["launches"] > 1000, "the calls did not reach the device library"
+    for key in ("ipower_cgj", "ipower_cg"):
+        assert cpu[key]["status"] == exact[key]["status"] == tree[key]["status"]
+        assert exact[key]["vals"] == cpu[key]["vals"] and exact[key]["its"] == cpu[key]["its"], key
+        assert exact[key]["vecs"] == cpu[key]["vecs"], key
+        np.testing.assert_allclose(tree[key]["vals"], cpu[key]["vals"], rtol=1e-4)
+    assert exact["regularize"]["status"] == cpu["regularize"]["status"] == tree["regularize"]["status"] == 0
+    assert exact["regularize"]["vertex"] == cpu["regularize"]["vertex"]
+    assert exact["regularize"]["iters"] == cpu["regularize"]["iters"]
+    assert abs(tree["regularize"]["iters"] - cpu["regularize"]["iters"]) <= max(1, 0.02 * cpu["regularize"]["iters"])
+    np.testing.assert_allclose(tree["regularize"]["vertex"], cpu["regularize"]["vertex"], rtol=0, atol=1e-9)
 
 
 def test_shim_entry_points_tolerate_concurrent_callers(nbgpu_lib):

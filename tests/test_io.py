@@ -1,6 +1,7 @@
 """On-disk formats (nbots_b200/io.py): the writers must produce the reference's bytes, the loaders must
 bring back what was written.  Fixtures under tests/golden/io/ were written by the reference itself
 (oracle/make_golden_io.py); with oracle/_ref present the comparison is repeated live."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -113,3 +114,27 @@ def test_writers_match_live_reference(tmp_path):
         assert read("a/m.vtk").replace(b"a/m_extra", b"b/m_extra") == read("b/m.vtk")
     finally:
         os.chdir(cwd)
+
+
+def test_nbt_header_matches_the_reference_writer(tmp_path):
+    """NBT (file_format_nbt.c): for triangle and quad meshes the reference writes the header only and its reader
+    reports failure on the (unimplemented) data section; both behaviours are mirrored."""
+    for kind, name in ((0, "grid_trg.nbt"), (1, "grid_quad.nbt")):
+        m = meshgen.structured_mesh(4, 3, 2.0, 1.0, kind=kind)
+        out = str(tmp_path / name)
+        assert io.save_nbt(out, m) == 0
+        assert read(out) == read(os.path.join(GOLD, name))          # byte-identical to nb_mesh2D_save_nbt
+        assert io.read_nbt_type(os.path.join(GOLD, name)) == (0, kind)
+        assert io.load_nbt(os.path.join(GOLD, name), kind) == 1     # as nb_mesh2D_read_nbt
+        assert io.load_nbt(os.path.join(GOLD, name), 1 - kind) == 1
+    assert io.read_nbt_type(str(tmp_path / "missing.nbt")) == (1, None)
+    assert io.read_nbt_type(os.path.join(GOLD, "grid_quad.vtk")) == (1, None)
+    assert io.save_nbt(str(tmp_path / "no_such_dir" / "x.nbt"), m) == 1
+    if ref.available():
+        L = ref.lib()
+        t = C.c_int(-1)
+        assert L.refh_mesh_read_type_nbt(os.path.join(GOLD, "grid_quad.nbt").encode(), C.byref(t)) == 0 and t.value == 1
+        rm = ref.RefMesh.from_arrays(m)
+        assert L.refh_mesh_read_nbt(rm.h, os.path.join(GOLD, "grid_quad.nbt").encode()) == 1
+        assert L.refh_mesh_save_nbt(rm.h, str(tmp_path / "r.nbt").encode()) == 0
+        assert read(str(tmp_path / "r.nbt")) == read(os.path.join(GOLD, "grid_quad.nbt"))
