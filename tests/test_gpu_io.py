@@ -24,14 +24,14 @@ def test_solve_a_reference_written_mat4_system_end_to_end(nbgpu_lib, tmp_path, s
     path = str(tmp_path / "sys.mat")
     shutil.copy(os.path.join(GOLD, "lap9_5.mat"), path)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "solve_file.py"), path, "--solver", solver,
-                          "--rel-tol", "1e-10"], capture_output=True, text=True, timeout=600)
+                          "--rel-tol", "1e-10", "--max-iter", "500"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     rec = io.load_mat4(path)
     rs, cols, vals = rec["A"]
     b, x = rec["b"], rec["x"]
     K = port.Csr(rs, cols, vals)
     tol = 1e-10 * float(np.linalg.norm(b))
-    ost, ox, oit, ores = (K.pcg_jacobi if solver == "pcg" else K.cg)(b, tol=tol)
+    ost, ox, oit, ores = (K.pcg_jacobi if solver == "pcg" else K.cg)(b, tol=tol, max_iter=500)
     assert ost == 0 and rel_l2(x, ox) <= 1e-10
     assert np.linalg.norm(K.spmv(x) - b) <= 2 * tol
     it = int(out.stdout.split("iterations=")[1].split()[0])
