@@ -225,6 +225,134 @@ assemble_gather_kernel(uint32_t n_rows, uint32_t col_shift, const double *__rest
 	F[row] = f_acc;
 }
 
+// ---- GATHER, node-parallel: one thread per NODE (both of its rows) ------------------------
+// For matrices in the 2x2-blocked layout (every mesh-built FEM matrix).  Against the row-parallel
+// kernel above: the Jacobians and gradients of an element are shared by the node's two rows (4x
+// instead of 8x redundant integration for quads), the node's block ids (one per 2x2 block, read once,
+// coalesced, from bcol) replace 32 linear searches through the per-entry column array per element,
+// and the two rows are accumulated in shared memory and written ONCE -- no memset of K, no
+// read-modify-write per contributing element.  Every entry still receives its contributions from 0
+// upwards in ascending element id, each of them summed over the Gauss points in order, so K and F
+// keep the reference's bits (pipeline.c:174-264).
+constexpr int kNodeThreads = 128;   // 8 slices per CTA
+constexpr int kNodeMaxBlocks = 24;  // 2x2 blocks per node row held in (dynamic) shared memory: 36 bytes per block and thread
+
+template <int NPE, int NGP>
+__global__ void __launch_bounds__(kNodeThreads)
+assemble_node_kernel(uint32_t n_rows, uint32_t col_shift, uint32_t nb_max, const double *__restrict__ nod,
+		     const uint32_t *__restrict__ adj, const uint32_t *__restrict__ n2e_ptr,
+		     const uint32_t *__restrict__ n2e, const uint8_t *__restrict__ enabled,
+		     const double *__restrict__ scale, AsmParams P, const uint32_t *__restrict__ slice_off,
+		     const uint32_t *__restrict__ perm, const uint32_t *__restrict__ bcol, double *__restrict__ val,
+		     double *__restrict__ F, unsigned int *first_bad, int *pattern_miss)
+{
+	// dynamic shared memory: double acc[4 nb_max][threads] | uint32 id[nb_max][threads]
+	extern __shared__ __align__(16) unsigned char node_smem[];
+	double(*s_acc)[kNodeThreads] = reinterpret_cast<double(*)[kNodeThreads]>(node_smem);
+	uint32_t(*s_id)[kNodeThreads] =
+		reinterpret_cast<uint32_t(*)[kNodeThreads]>(node_smem + (size_t)4 * nb_max * kNodeThreads * sizeof(double));
+	const uint32_t tid = threadIdx.x;
+	const uint32_t pair = blockIdx.x * kNodeThreads + tid;   // storage pair: slice * 16 + nl
+	const uint32_t slice = pair >> 4, nl = pair & 15;
+	const uint32_t spos = slice * kSliceRows + 2 * nl;
+	if (spos >= ((n_rows + kSliceRows - 1) / kSliceRows) * kSliceRows)
+		return;
+	const uint32_t row0 = perm ? perm[spos] : spos;
+	if (row0 >= n_rows)
+		return;
+	const uint32_t node = (row0 + col_shift) >> 1;
+	const uint32_t off = slice_off[slice], nb = (slice_off[slice + 1] - off) >> 1;
+	for (uint32_t jb = 0; jb < nb; jb++) {
+		s_id[jb][tid] = bcol[((size_t)(off >> 1) + jb) * 16u + nl];
+#pragma unroll
+		for (int q = 0; q < 4; q++)
+			s_acc[jb * 4 + q][tid] = 0.0;
+	}
+	double f0 = 0.0, f1 = 0.0;
+	for (uint32_t t = n2e_ptr[node]; t < n2e_ptr[node + 1]; t++) {
+		const uint32_t e = n2e[t];
+		uint32_t v[NPE];
+		double xs[NPE], ys[NPE];
+		int li = 0;
+#pragma unroll
+		for (int i = 0; i < NPE; i++) {
+			v[i] = adj[(size_t)e * NPE + i];
+			xs[i] = nod[2 * (size_t)v[i]];
+			ys[i] = nod[2 * (size_t)v[i] + 1];
+		}
+#pragma unroll
+		for (int i = NPE - 1; i >= 0; i--)
+			if (v[i] == node)
+				li = i;   // first local index of this node
+		double D[4], rho;
+		element_material(P, enabled, scale, e, D, rho);
+		const double fx = P.self_weight ? P.gx * rho : 0.0, fy = P.self_weight ? P.gy * rho : 0.0;
+		double k0[2 * NPE], k1[2 * NPE];   // rows (2 li) and (2 li + 1) of Ke
+#pragma unroll
+		for (int c = 0; c < 2 * NPE; c++)
+			k0[c] = k1[c] = 0.0;
+		double fe0 = 0.0, fe1 = 0.0;
+		bool bad = false;
+#pragma unroll
+		for (int gp = 0; gp < NGP; gp++) {
+			double dx[NPE], dy[NPE];
+			const double detJ = jacobian_gradients<NPE, NGP>(xs, ys, gp, dx, dy);
+			if (detJ < 0)
+				bad = true;   // utils.c:44-47
+			const double wp = c_tab.w[gp];
+			double dxi = dx[0], dyi = dy[0], Ni = c_tab.Ni[gp];
+#pragma unroll
+			for (int i = 1; i < NPE; i++)
+				if (li == i) {
+					dxi = dx[i];
+					dyi = dy[i];
+					Ni = c_tab.Ni[i * NGP + gp];
+				}
+#pragma unroll
+			for (int j = 0; j < NPE; j++) {
+				// pipeline.c:196-214, the 2x2 block (li, j)
+				k0[2 * j] += (dxi * dx[j] * D[0] + dyi * dy[j] * D[3]) * detJ * P.thickness * wp;
+				k0[2 * j + 1] += (dxi * dy[j] * D[1] + dyi * dx[j] * D[3]) * detJ * P.thickness * wp;
+				k1[2 * j] += (dyi * dx[j] * D[1] + dxi * dy[j] * D[3]) * detJ * P.thickness * wp;
+				k1[2 * j + 1] += (dyi * dy[j] * D[2] + dxi * dx[j] * D[3]) * detJ * P.thickness * wp;
+			}
+			const double integral = Ni * detJ * P.thickness * wp;   // pipeline.c:225-228
+			fe0 += integral * fx;
+			fe1 += integral * fy;
+		}
+		if (bad) {
+			atomicMin(first_bad, e);
+			continue;
+		}
+#pragma unroll
+		for (int j = 0; j < NPE; j++) {
+			uint32_t jb = 0;
+			while (jb < nb && s_id[jb][tid] != v[j])
+				jb++;
+			if (jb == nb) {
+				*pattern_miss = 1;   // sparse.c:213-217
+				continue;
+			}
+			s_acc[jb * 4 + 0][tid] += k0[2 * j];
+			s_acc[jb * 4 + 1][tid] += k0[2 * j + 1];
+			s_acc[jb * 4 + 2][tid] += k1[2 * j];
+			s_acc[jb * 4 + 3][tid] += k1[2 * j + 1];
+		}
+		f0 += fe0;
+		f1 += fe1;
+	}
+	const uint32_t lane = spos & 31;
+	for (uint32_t jb = 0; jb < nb; jb++) {
+		double *p = val + ((size_t)off + 2 * jb) * kSliceRows + lane;
+		p[0] = s_acc[jb * 4 + 0][tid];
+		p[kSliceRows] = s_acc[jb * 4 + 1][tid];
+		p[1] = s_acc[jb * 4 + 2][tid];
+		p[kSliceRows + 1] = s_acc[jb * 4 + 3][tid];
+	}
+	F[row0] = f0;
+	F[row0 + 1] = f1;
+}
+
 // ---- ATOMIC / COLOR: one thread per element --------------------------------
 template <int NPE, int NGP, bool ATOMIC>
 __global__ void __launch_bounds__(128)
@@ -597,13 +725,28 @@ int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int 
 		    const double *d_scale, double *d_F, unsigned int *d_bad, int *d_miss)
 {
 	Context &c = ctx();
-	if (mode == NBGPU_ASSEMBLY_GATHER) {
+	if (mode == NBGPU_ASSEMBLY_GATHER && K->blocked && K->max_width <= 2 * kNodeMaxBlocks && (K->N & 1u) == 0 &&
+	    !getenv("NBGPU_ASSEMBLY_ROWS")) {
+		// node-parallel form: overwrites every entry of the rows, no reset needed
+		const uint32_t pairs = K->n_slices * 16u;
+		const uint32_t nb_max = (K->max_width + 1) / 2;
+		const size_t smem = (size_t)nb_max * kNodeThreads * (4 * sizeof(double) + sizeof(uint32_t));
+		if (smem > 48 * 1024)
+			NB_CUDA(cudaFuncSetAttribute(assemble_node_kernel<NPE, NGP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+						     (int)smem));
+		assemble_node_kernel<NPE, NGP><<<(pairs + kNodeThreads - 1) / kNodeThreads, kNodeThreads, smem, c.stream>>>(
+			K->N, K->col_shift, nb_max, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, P, K->d_slice_off,
+			K->d_perm, K->d_bcol, K->d_val, d_F, d_bad, d_miss);
+		NB_LAUNCHED();
+	} else if (mode == NBGPU_ASSEMBLY_GATHER) {
+		NB_CUDA(cudaMemsetAsync(K->d_val, 0, K->stored * sizeof(double), c.stream));   // nb_sparse_reset (pipeline.c:54)
 		const uint32_t rows = K->n_slices * kSliceRows;
 		assemble_gather_kernel<NPE, NGP><<<(rows + kBlock - 1) / kBlock, kBlock, 0, c.stream>>>(
 			K->N, K->col_shift, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, P, K->d_slice_off,
 			K->d_perm, K->d_col, K->d_val, d_F, d_bad, d_miss);
 		NB_LAUNCHED();
 	} else if (mode == NBGPU_ASSEMBLY_ATOMIC) {
+		NB_CUDA(cudaMemsetAsync(K->d_val, 0, K->stored * sizeof(double), c.stream));
 		NB_CUDA(cudaMemsetAsync(d_F, 0, 2 * (size_t)m->N_nod * sizeof(double), c.stream));
 		assemble_element_kernel<NPE, NGP, true><<<(m->N_elems + 127) / 128, 128, 0, c.stream>>>(
 			m->N_elems, nullptr, m->d_nod, m->d_adj, d_en, d_scale, P, K->d_slice_off, K->d_inv_perm,
@@ -611,6 +754,7 @@ int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int 
 		NB_LAUNCHED();
 	} else {
 		NB_TRY(build_coloring(m));
+		NB_CUDA(cudaMemsetAsync(K->d_val, 0, K->stored * sizeof(double), c.stream));
 		NB_CUDA(cudaMemsetAsync(d_F, 0, 2 * (size_t)m->N_nod * sizeof(double), c.stream));
 		for (uint32_t col = 0; col < m->n_colors; col++) {
 			const uint32_t n = m->color_ptr[col + 1] - m->color_ptr[col];
@@ -810,8 +954,7 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
 	NB_CUDA(nbgpu::dmalloc(&d_flags, 2 * sizeof(unsigned int)));
 	const unsigned int init_flags[2] = {0xFFFFFFFFu, 0u};
 	NB_CUDA(cudaMemcpyAsync(d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, c.stream));
-	// nb_sparse_reset (pipeline.c:54) -- F is zeroed/overwritten by the kernels (pipeline.c:57)
-	NB_CUDA(cudaMemsetAsync(K->d_val, 0, K->stored * sizeof(double), c.stream));
+	// nb_sparse_reset (pipeline.c:54) and the zeroing of F (pipeline.c:57) are done by the schedules themselves
 	int st;
 	if (m->npe == 3)
 		st = launch_assembly<3, 1>(K, m, P, params->mode, d_en, d_scale, d_F, d_flags, (int *)(d_flags + 1));
