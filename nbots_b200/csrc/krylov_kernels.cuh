@@ -276,9 +276,13 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 }
 
 // CLASSIC K2: g += a w, q = g / diag, gq' = g.q, gg' = g.g   (:64-68; x += a p is done by K3)
-// Two elements per thread and trip, every load of a trip issued before the first
-// use; the first trip's g, diag are loaded before the dependency wait (the
-// SpMV kernel running ahead of us only writes w and the scalars).
+// kVecBatch elements per thread and trip (a grid-stride apart, so every access is coalesced), every load
+// of a trip issued before the first use.  The first trip's g, diag are loaded BEFORE the dependency wait
+// (the SpMV kernel running ahead of us only writes w and the scalars) and its w right after the wait,
+// ahead of the reduction of K1's partials: one round trip to L2 between the wait and the first store.
+// At 1 M dof the resident grid covers the vector in a single trip.
+constexpr int kVecBatch = 4;
+
 template <bool JACOBI, typename Comm>
 __global__ void __launch_bounds__(kBlock)
 krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev, unsigned long long seq_red,
@@ -287,15 +291,12 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
-	double g0 = 0, d0 = 1, g1 = 0, d1 = 1;
-	if (base < N) {
-		const uint32_t j1 = base + stride < N ? base + stride : base;
-		g0 = g[base];
-		g1 = g[j1];
-		if (JACOBI) {
-			d0 = diag[base];
-			d1 = diag[j1];
-		}
+	double gv[kVecBatch], dv[kVecBatch], wv[kVecBatch];
+#pragma unroll
+	for (int b = 0; b < kVecBatch; b++) {
+		const uint64_t i = (uint64_t)base + (uint64_t)b * stride;
+		gv[b] = i < N ? g[i] : 0.0;
+		dv[b] = (JACOBI && i < N) ? diag[i] : 1.0;
 	}
 	pdl_wait();
 	pdl_launch_dependents();
@@ -304,6 +305,11 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 	double pw_k = st->pw;
 	if (done)
 		return;
+#pragma unroll
+	for (int b = 0; b < kVecBatch; b++) {
+		const uint64_t i = (uint64_t)base + (uint64_t)b * stride;
+		wv[b] = i < N ? w[i] : 0.0;
+	}
 	if (Comm::kDist) {
 		// every CTA collects the ranks' partials of K1 itself (dist_comm.cuh)
 		double t[1];
@@ -325,35 +331,28 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 	}
 	const double alpha = __ddiv_rn(gq_k, pw_k);
 	double dots[2] = {0.0, 0.0};
-	for (uint32_t i0 = base; i0 < N; i0 += 2 * stride) {
-		const uint32_t i1 = i0 + stride;
-		const bool has1 = i1 < N;
-		const uint32_t j1 = has1 ? i1 : i0;
+	for (uint64_t i0 = base; i0 < N; i0 += (uint64_t)kVecBatch * stride) {
 		if (i0 != base) {
-			g0 = g[i0];
-			g1 = g[j1];
-			if (JACOBI) {
-				d0 = diag[i0];
-				d1 = diag[j1];
+#pragma unroll
+			for (int b = 0; b < kVecBatch; b++) {
+				const uint64_t i = i0 + (uint64_t)b * stride;
+				gv[b] = i < N ? g[i] : 0.0;
+				dv[b] = (JACOBI && i < N) ? diag[i] : 1.0;
+				wv[b] = i < N ? w[i] : 0.0;
 			}
 		}
-		const double w0 = w[i0], w1 = w[j1];
-		const double gn0 = __dadd_rn(g0, __dmul_rn(alpha, w0));
-		const double gn1 = __dadd_rn(g1, __dmul_rn(alpha, w1));
-		g[i0] = gn0;
-		dots[0] = __dadd_rn(dots[0], __dmul_rn(gn0, gn0));
-		if (JACOBI) {
-			const double q0 = __ddiv_rn(gn0, d0);
-			q[i0] = q0;
-			dots[1] = __dadd_rn(dots[1], __dmul_rn(gn0, q0));
-		}
-		if (has1) {
-			g[i1] = gn1;
-			dots[0] = __dadd_rn(dots[0], __dmul_rn(gn1, gn1));
+#pragma unroll
+		for (int b = 0; b < kVecBatch; b++) {
+			const uint64_t i = i0 + (uint64_t)b * stride;
+			if (i >= N)
+				break;
+			const double gn = __dadd_rn(gv[b], __dmul_rn(alpha, wv[b]));
+			g[i] = gn;
+			dots[0] = __dadd_rn(dots[0], __dmul_rn(gn, gn));
 			if (JACOBI) {
-				const double q1 = __ddiv_rn(gn1, d1);
-				q[i1] = q1;
-				dots[1] = __dadd_rn(dots[1], __dmul_rn(gn1, q1));
+				const double qn = __ddiv_rn(gn, dv[b]);
+				q[i] = qn;
+				dots[1] = __dadd_rn(dots[1], __dmul_rn(gn, qn));
 			}
 		}
 	}
@@ -380,7 +379,7 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 
 // CLASSIC K3: x += a p (:62-63, moved here from K2: p is read once per iteration instead of twice; same
 // operations, same rounding), then p = -q + b p (:70-74); plain CG passes q == g.  p and x are
-// preloaded before the dependency wait (the update kernel ahead of us writes neither).
+// preloaded before the dependency wait (the update kernel ahead of us writes neither), q right after it.
 template <typename Comm>
 __global__ void __launch_bounds__(kBlock)
 krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev, const double *q,
@@ -389,13 +388,12 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
-	double p0 = 0, p1 = 0, x0 = 0, x1 = 0;
-	if (base < N) {
-		const uint32_t j1 = base + stride < N ? base + stride : base;
-		p0 = p[base];
-		p1 = p[j1];
-		x0 = x[base];
-		x1 = x[j1];
+	double pv[kVecBatch], xv[kVecBatch], qv[kVecBatch];
+#pragma unroll
+	for (int b = 0; b < kVecBatch; b++) {
+		const uint64_t i = (uint64_t)base + (uint64_t)b * stride;
+		pv[b] = i < N ? p[i] : 0.0;
+		xv[b] = i < N ? x[i] : 0.0;
 	}
 	pdl_wait();
 	pdl_launch_dependents();
@@ -405,6 +403,11 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 	const double pw_k = st->pw;
 	if (done)
 		return;
+#pragma unroll
+	for (int b = 0; b < kVecBatch; b++) {
+		const uint64_t i = (uint64_t)base + (uint64_t)b * stride;
+		qv[b] = i < N ? q[i] : 0.0;
+	}
 	if (Comm::kDist) {
 		double t[2];
 		if (!comm.template collect<2>(seq_prev, t)) {
@@ -428,22 +431,23 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 	}
 	const double alpha = __ddiv_rn(gq_k, pw_k);
 	const double beta = __ddiv_rn(gq_n, gq_k);
-	for (uint32_t i0 = base; i0 < N; i0 += 2 * stride) {
-		const uint32_t i1 = i0 + stride;
-		const bool has1 = i1 < N;
-		const uint32_t j1 = has1 ? i1 : i0;
+	for (uint64_t i0 = base; i0 < N; i0 += (uint64_t)kVecBatch * stride) {
 		if (i0 != base) {
-			p0 = p[i0];
-			p1 = p[j1];
-			x0 = x[i0];
-			x1 = x[j1];
+#pragma unroll
+			for (int b = 0; b < kVecBatch; b++) {
+				const uint64_t i = i0 + (uint64_t)b * stride;
+				pv[b] = i < N ? p[i] : 0.0;
+				xv[b] = i < N ? x[i] : 0.0;
+				qv[b] = i < N ? q[i] : 0.0;
+			}
 		}
-		const double q0 = q[i0], q1 = q[j1];
-		x[i0] = __dadd_rn(x0, __dmul_rn(alpha, p0));
-		p[i0] = __dadd_rn(-q0, __dmul_rn(beta, p0));
-		if (has1) {
-			x[i1] = __dadd_rn(x1, __dmul_rn(alpha, p1));
-			p[i1] = __dadd_rn(-q1, __dmul_rn(beta, p1));
+#pragma unroll
+		for (int b = 0; b < kVecBatch; b++) {
+			const uint64_t i = i0 + (uint64_t)b * stride;
+			if (i >= N)
+				break;
+			x[i] = __dadd_rn(xv[b], __dmul_rn(alpha, pv[b]));
+			p[i] = __dadd_rn(-qv[b], __dmul_rn(beta, pv[b]));
 		}
 	}
 }
@@ -765,7 +769,7 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 	const bool pdl = R.pdl && !seq;
 	double *partials = seq ? nullptr : R.partials;
 	const int64_t slice_blocks = ((int64_t)A->n_slices * 32 + kBlock - 1) / kBlock;
-	const int64_t vec_blocks = ((int64_t)N + 2 * kBlock - 1) / (2 * kBlock);
+	const int64_t vec_blocks = ((int64_t)N + kVecBatch * kBlock - 1) / (kVecBatch * kBlock);
 	int igrid = 0, sgrid = 0, ugrid = 0, dgrid = 0, fgrid = 0;
 	if (!stream) {
 		igrid = jacobi ? resident_grid(krylov_init_kernel<true>, slice_blocks)
@@ -777,8 +781,9 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 			       : resident_grid(krylov_update_kernel<false, Comm>, vec_blocks);
 		dgrid = resident_grid(krylov_dir_kernel<Comm>, vec_blocks);
 	} else {
-		fgrid = jacobi ? resident_grid(krylov_fupdate_kernel<true, Comm>, vec_blocks, true)
-			       : resident_grid(krylov_fupdate_kernel<false, Comm>, vec_blocks, true);
+		const int64_t pair_blocks = ((int64_t)N / 2 + kBlock) / kBlock;   // one 16-byte pair per thread and trip
+		fgrid = jacobi ? resident_grid(krylov_fupdate_kernel<true, Comm>, pair_blocks, true)
+			       : resident_grid(krylov_fupdate_kernel<false, Comm>, pair_blocks, true);
 	}
 
 	// ticketless reductions (single GPU, parallel-tree dots, streamed K1): see common.cuh
