@@ -191,6 +191,40 @@ __device__ __forceinline__ bool warp_wait_halo(const PeerTable &T, int which, un
 	return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 
+// (cold: called once per warp from inside the streaming loop; out of line it costs that loop no registers)
+static __device__ __noinline__ bool warp_wait_halo_cold(const PeerTable *T, int which, unsigned long long seq)
+{
+	return warp_wait_halo(*T, which, seq);
+}
+
+// CTA-wide: every rank's message `seq` from the slots in this GPU's own control block, summed in rank
+// order.  Kept out of line with scalar arguments only: inlined it costs the streaming kernels ~35
+// registers (a CTA per SM), as a member function the exchange policy object would be copied to every
+// thread's stack.
+template <int NV>
+__device__ __noinline__ bool collect_slots(DistControl *mine, int world, unsigned long long timeout_ns,
+					   unsigned long long seq, double (&v)[NV])
+{
+	__shared__ double s_val[NV][kMaxRanks];
+	int ok = 1;
+	if ((int)threadIdx.x < world * NV) {
+		const int r = threadIdx.x / NV, c = threadIdx.x % NV;
+		double got = 0.0;
+		ok = wait_msg(&mine->msg[seq & 1][r][c], seq, &got, mine, timeout_ns) ? 1 : 0;
+		s_val[c][r] = got;
+	}
+	if (!__syncthreads_and(ok))
+		return false;
+#pragma unroll
+	for (int c = 0; c < NV; c++) {
+		double t = 0.0;
+		for (int r = 0; r < world; r++)
+			t += s_val[c][r];
+		v[c] = t;
+	}
+	return true;
+}
+
 // ---- the two exchange policies of the solver kernels --------------------------------
 // A reduction over the ranks has a PRODUCER side (the CTA that finished the kernel's grid
 // reduction) and a CONSUMER side (the next kernel):
@@ -257,7 +291,7 @@ struct PeerComm {
 	}
 	__device__ __forceinline__ bool wait_halo(int which, unsigned long long seq) const
 	{
-		return warp_wait_halo(*T, which, seq);
+		return warp_wait_halo_cold(T, which, seq);
 	}
 
 	// thread (r, c) of the calling CTA posts value c to rank r
@@ -279,24 +313,7 @@ struct PeerComm {
 	template <int NV>
 	__device__ __forceinline__ bool collect(unsigned long long seq, double (&v)[NV]) const
 	{
-		__shared__ double s_val[NV][kMaxRanks];
-		int ok = 1;
-		if ((int)threadIdx.x < world * NV) {
-			const int r = threadIdx.x / NV, c = threadIdx.x % NV;
-			double got = 0.0;
-			ok = wait_msg(&mine->msg[seq & 1][r][c], seq, &got, mine, timeout_ns) ? 1 : 0;
-			s_val[c][r] = got;
-		}
-		if (!__syncthreads_and(ok))
-			return false;
-#pragma unroll
-		for (int c = 0; c < NV; c++) {
-			double t = 0.0;
-			for (int r = 0; r < world; r++)
-				t += s_val[c][r];
-			v[c] = t;
-		}
-		return true;
+		return collect_slots<NV>(mine, world, timeout_ns, seq, v);
 	}
 	template <int NV>
 	__device__ __noinline__ bool all_reduce(double (&v)[NV], unsigned long long seq) const

@@ -284,7 +284,7 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 constexpr int kVecBatch = 4;
 
 template <bool JACOBI, typename Comm>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)
 krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev, unsigned long long seq_red,
 		     const double *w, const double *__restrict__ diag, double *__restrict__ g,
 		     double *__restrict__ q, double *partials, KrylovState *st, uint32_t n_prev, int ticketless)
