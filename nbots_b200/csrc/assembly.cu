@@ -450,14 +450,26 @@ assemble_element_kernel(uint32_t n_work, const uint32_t *__restrict__ work /* nu
 
 // ---- boundary conditions ---------------------------------------------------
 
-// F[dof[k]] += add[k] in list order.  The lists are boundary-sized; one thread
-// keeps the order of the reference's sequential adds (set_bconditions.c:156-170).
-__global__ void vector_add_entries_kernel(double *F, uint32_t n, const uint32_t *__restrict__ dof,
-					  const double *__restrict__ add)
+// F[dof[k]] += add[k] in list order (set_bconditions.c:156-170).  Entries of different dofs commute; the
+// entries of ONE dof are added by one thread in list order: thread k owns dof[k] if no earlier entry names
+// the same dof, and then walks the rest of the list.  The lists are boundary-sized (thousands of entries),
+// so the quadratic scan is a few microseconds -- the single-thread loop this replaces took 215 us for the
+// 4000 entries of the Q1 workload, as long as the assembly itself.
+__global__ void __launch_bounds__(256)
+vector_add_entries_kernel(double *F, uint32_t n, const uint32_t *__restrict__ dof, const double *__restrict__ add)
 {
-	if (blockIdx.x == 0 && threadIdx.x == 0)
-		for (uint32_t k = 0; k < n; k++)
-			F[dof[k]] += add[k];
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n)
+		return;
+	const uint32_t d = dof[k];
+	for (uint32_t j = 0; j < k; j++)
+		if (dof[j] == d)
+			return;
+	double acc = F[d];
+	for (uint32_t j = k; j < n; j++)
+		if (dof[j] == d)
+			acc += add[j];
+	F[d] = acc;
 }
 
 // nb_sparse_set_Dirichlet_condition applied for a whole ordered list at once.
@@ -996,7 +1008,7 @@ int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof, const
 	if (e == cudaSuccess)
 		e = cudaMemcpyAsync(d_dof, dof, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream);
 	if (e == cudaSuccess) {
-		vector_add_entries_kernel<<<1, 32, 0, c.stream>>>(d_F, n, d_dof, d_add);
+		vector_add_entries_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(d_F, n, d_dof, d_add);
 		ctx().launches++;
 		e = cudaGetLastError();
 	}
@@ -1119,7 +1131,7 @@ int nbgpu_vector_add_entries_dev(double *d_F, uint32_t n, const uint32_t *d_dof,
 	if (n == 0)
 		return NBGPU_OK;
 	NB_ARG(d_F != nullptr && d_dof != nullptr && d_add != nullptr);
-	vector_add_entries_kernel<<<1, 32, 0, ctx().stream>>>(d_F, n, d_dof, d_add);
+	vector_add_entries_kernel<<<(n + 255) / 256, 256, 0, ctx().stream>>>(d_F, n, d_dof, d_add);
 	NB_LAUNCHED();
 	return NBGPU_OK;
 }
