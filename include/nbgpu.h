@@ -202,6 +202,20 @@ int nbgpu_mesh_create(uint32_t N_nod, const double *nod, uint32_t N_elems,
 		      nbgpu_mesh_t **out);
 int nbgpu_mesh_destroy(nbgpu_mesh_t *mesh);
 
+/* The same pattern built ON THE DEVICE from a device-resident mesh, straight into
+ * the SELL-32 column arrays (2 dofs per node, values zero): nothing is built on
+ * the host or uploaded.  edg (host array) may be NULL; if given,
+ * every edge must be an element side.  Returns NBGPU_OK with *out == NULL when
+ * the pattern does not qualify for the device path (ragged rows that want the
+ * sigma-sorted layout, an edge that is no element side, or one of the layout
+ * override switches): use nbgpu_pattern_from_mesh + nbgpu_matrix_create_from_csr
+ * then. */
+int nbgpu_matrix_create_from_mesh(const nbgpu_mesh_t *mesh, uint32_t N_edg,
+				  const uint32_t *edg, nbgpu_matrix_t **out);
+/* number of colours of the device-built element colouring the COLOR schedule
+ * uses (built on first use); colors[N_elems] gets each element's colour if not NULL */
+int nbgpu_mesh_coloring(nbgpu_mesh_t *mesh, uint32_t *n_colors, uint8_t *colors);
+
 /* element tables as struct nb_fem_elem_s holds them (element_struct.h:8-16),
  * indexed [node * N_gp + gp] (element.c:144-160) */
 typedef struct {

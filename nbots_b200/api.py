@@ -227,6 +227,22 @@ class Mesh:
         check(lib().nbgpu_mesh_create(m.n_nod, _ptr(m.nod, f64p), m.n_elems, m.npe, _ptr(m.adj, u32p), C.byref(h)))
         self.h = h.value
 
+    def create_matrix(self, with_edges=True):
+        """nbgpu_matrix_create_from_mesh: the pattern built on the device -> Matrix, or None when the mesh does
+        not qualify for the device path (then: pattern_from_mesh + Matrix.from_csr)."""
+        h = C.c_void_p()
+        m = self.m
+        edg = m.edg if with_edges else None
+        check(lib().nbgpu_matrix_create_from_mesh(self.h, m.n_edg if with_edges else 0, _ptr(edg, u32p), C.byref(h)))
+        return Matrix(h.value) if h.value else None
+
+    def coloring(self):
+        """(n_colors, colour of every element) of the device-built element colouring."""
+        n = C.c_uint32(0)
+        colors = np.zeros(max(1, self.m.n_elems), dtype=np.uint8)
+        check(lib().nbgpu_mesh_coloring(self.h, C.byref(n), _ptr(colors, u8p)))
+        return n.value, colors[:self.m.n_elems]
+
     def assemble(self, K: Matrix, d_F: DeviceBuffer, E, nu, density=0.0, self_weight=False, gravity=(0.0, 0.0),
                  analysis=0, thickness=1.0, enabled=None, elem_scale=None, mode=capi.ASSEMBLY_GATHER):
         p = capi.AssemblyParams()

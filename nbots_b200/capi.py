@@ -104,6 +104,8 @@ SIGNATURES = {
                                           u32p, u32p, u64p]),
     "nbgpu_mesh_create": (C.c_int, [C.c_uint32, f64p, C.c_uint32, C.c_uint32, u32p, vpp]),
     "nbgpu_mesh_destroy": (C.c_int, [C.c_void_p]),
+    "nbgpu_matrix_create_from_mesh": (C.c_int, [C.c_void_p, C.c_uint32, u32p, vpp]),
+    "nbgpu_mesh_coloring": (C.c_int, [C.c_void_p, u32p, u8p]),
     "nbgpu_elem_tables_default": (C.c_int, [C.c_uint32, C.POINTER(ElemTables)]),
     "nbgpu_constitutive_matrix": (C.c_int, [C.c_double, C.c_double, C.c_int, f64p]),
     "nbgpu_assemble_elasticity2d": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ElemTables),

@@ -31,22 +31,9 @@
 #include <cstring>
 
 #include "matrix.cuh"
+#include "mesh.cuh"
 
 using namespace nbgpu;
-
-struct nbgpu_mesh_s {
-	uint32_t N_nod = 0, N_elems = 0, npe = 0;
-	double *d_nod = nullptr;          // [2 N_nod]
-	uint32_t *d_adj = nullptr;        // [npe N_elems]
-	uint32_t *d_n2e_ptr = nullptr;    // [N_nod + 1] elements around each node ...
-	uint32_t *d_n2e = nullptr;        // [npe N_elems] ... ascending element id
-	uint8_t *d_enabled = nullptr;     // [N_elems] scratch for the enabled mask
-	double *d_scale = nullptr;        // [N_elems] scratch for per-element factors
-	std::vector<uint32_t> h_adj;      // host copy (colouring is built lazily)
-	uint32_t n_colors = 0;
-	std::vector<uint32_t> color_ptr;  // [n_colors + 1]
-	uint32_t *d_color_elems = nullptr;
-};
 
 namespace {
 
@@ -694,42 +681,163 @@ int upload_tables(const nbgpu_elem_tables_t *t, uint32_t npe)
 	return NBGPU_OK;
 }
 
-// greedy colouring in element order: colour(e) = lowest colour not yet used by
-// an element sharing a node with e
+// ---- element colouring on the device (the reference has no colouring code) ----------
+// Jones-Plassmann rounds: an uncoloured element whose priority (a hash of its id, ties by id) is the largest
+// among its uncoloured neighbours -- the elements it shares a node with, found through the node -> element
+// lists -- takes the lowest colour none of its coloured neighbours uses.  Two neighbours can never both be
+// local maxima, so no two elements of a colour share a node.  A dozen rounds at a few microseconds each;
+// the host only reads the count of elements still uncoloured.
+__device__ __forceinline__ uint32_t color_priority(uint32_t e)
+{
+	uint32_t h = e * 2654435761u;
+	h ^= h >> 15;
+	h *= 2246822519u;
+	h ^= h >> 13;
+	return h;
+}
+
+__global__ void __launch_bounds__(256)
+color_round_kernel(uint32_t N_elems, uint32_t npe, const uint32_t *__restrict__ adj, const uint32_t *__restrict__ n2e_ptr,
+		   const uint32_t *__restrict__ n2e, const uint8_t *__restrict__ color, uint8_t *__restrict__ color_out,
+		   unsigned int *remaining, int *overflow)
+{
+	// decisions are taken on the colours of the PREVIOUS round only (color), so the result does not depend
+	// on the order in which the threads of a round run
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= N_elems)
+		return;
+	color_out[e] = color[e];
+	if (color[e] != 0xFF)
+		return;
+	const uint32_t pe = color_priority(e);
+	unsigned long long used = 0;
+	bool is_max = true;
+	for (uint32_t i = 0; i < npe && is_max; i++) {
+		const uint32_t v = adj[(size_t)e * npe + i];
+		for (uint32_t t = n2e_ptr[v]; t < n2e_ptr[v + 1]; t++) {
+			const uint32_t f = n2e[t];
+			if (f == e)
+				continue;
+			const uint8_t cf = color[f];
+			if (cf == 0xFF) {
+				const uint32_t pf = color_priority(f);
+				if (pf > pe || (pf == pe && f > e)) {
+					is_max = false;
+					break;
+				}
+			} else {
+				used |= 1ull << cf;
+			}
+		}
+	}
+	if (!is_max) {
+		atomicAdd(remaining, 1u);
+		return;
+	}
+	if (~used == 0) {
+		*overflow = 1;
+		return;
+	}
+	color_out[e] = (uint8_t)__ffsll((long long)~used) - 1;
+}
+
+__global__ void __launch_bounds__(256)
+color_count_kernel(uint32_t N_elems, const uint8_t *__restrict__ color, unsigned int *counts)
+{
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < N_elems)
+		atomicAdd(counts + color[e], 1u);
+}
+
+// elements of one colour never touch the same entry, so their order inside the colour's list does not matter
+__global__ void __launch_bounds__(256)
+color_scatter_kernel(uint32_t N_elems, const uint8_t *__restrict__ color, unsigned int *next, uint32_t *__restrict__ elems)
+{
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < N_elems)
+		elems[atomicAdd(next + color[e], 1u)] = e;
+}
+
 int build_coloring(nbgpu_mesh_t *m)
 {
 	if (m->n_colors)
 		return NBGPU_OK;
-	std::vector<uint64_t> used(m->N_nod, 0);
-	std::vector<uint8_t> color(m->N_elems);
-	uint32_t n_colors = 0;
-	for (uint32_t e = 0; e < m->N_elems; e++) {
-		uint64_t mask = 0;
-		for (uint32_t i = 0; i < m->npe; i++)
-			mask |= used[m->h_adj[(size_t)e * m->npe + i]];
-		if (~mask == 0) {
-			set_error("element colouring needs more than 64 colours");
-			return NBGPU_ERR_ARG;
-		}
-		const uint32_t cidx = (uint32_t)__builtin_ctzll(~mask);
-		color[e] = (uint8_t)cidx;
-		n_colors = std::max(n_colors, cidx + 1);
-		for (uint32_t i = 0; i < m->npe; i++)
-			used[m->h_adj[(size_t)e * m->npe + i]] |= 1ull << cidx;
+	Context &c = ctx();
+	uint8_t *d_color = nullptr, *d_color2 = nullptr;
+	unsigned int *d_cnt = nullptr;   // [0] remaining, [1] overflow, [2..66) per-colour counters
+	NB_CUDA(nbgpu::dmalloc(&d_color, 2 * std::max<size_t>(1, m->N_elems)));
+	d_color2 = d_color + std::max<size_t>(1, m->N_elems);
+	cudaError_t e = nbgpu::dmalloc(&d_cnt, 66 * sizeof(unsigned int));
+	if (e != cudaSuccess) {
+		nbgpu::dfree(d_color);
+		NB_CUDA(e);
 	}
+	uint8_t *const d_color_block = d_color;
+	auto done = [&](int st) {
+		if (st != NBGPU_OK)
+			nbgpu::dfree(d_color_block);
+		nbgpu::dfree(d_cnt);
+		return st;
+	};
+	cudaMemsetAsync(d_color, 0xFF, m->N_elems, c.stream);
+	const int grid = (int)((m->N_elems + 255) / 256);
+	unsigned int h_cnt[66];
+	for (int round = 0;; round++) {
+		cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), c.stream);
+		color_round_kernel<<<grid, 256, 0, c.stream>>>(m->N_elems, m->npe, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_color, d_color2,
+							       d_cnt, (int *)(d_cnt + 1));
+		c.launches++;
+		std::swap(d_color, d_color2);
+		e = cudaMemcpyAsync(h_cnt, d_cnt, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(c.stream);
+		if (e != cudaSuccess) {
+			set_error("colouring: %s", cudaGetErrorString(e));
+			return done(NBGPU_ERR_CUDA);
+		}
+		if (h_cnt[1] || round > 4096) {
+			set_error("element colouring needs more than 64 colours");
+			return done(NBGPU_ERR_ARG);
+		}
+		if (h_cnt[0] == 0)
+			break;
+	}
+	cudaMemsetAsync(d_cnt, 0, 66 * sizeof(unsigned int), c.stream);
+	color_count_kernel<<<grid, 256, 0, c.stream>>>(m->N_elems, d_color, d_cnt + 2);
+	c.launches++;
+	e = cudaMemcpyAsync(h_cnt, d_cnt, 66 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(c.stream);
+	if (e != cudaSuccess) {
+		set_error("colouring: %s", cudaGetErrorString(e));
+		return done(NBGPU_ERR_CUDA);
+	}
+	uint32_t n_colors = 0;
+	for (uint32_t k = 0; k < 64; k++)
+		if (h_cnt[2 + k])
+			n_colors = k + 1;
 	m->color_ptr.assign(n_colors + 1, 0);
-	for (uint32_t e = 0; e < m->N_elems; e++)
-		m->color_ptr[color[e] + 1]++;
-	for (uint32_t c = 0; c < n_colors; c++)
-		m->color_ptr[c + 1] += m->color_ptr[c];
-	std::vector<uint32_t> next(m->color_ptr.begin(), m->color_ptr.end() - 1), elems(m->N_elems);
-	for (uint32_t e = 0; e < m->N_elems; e++)
-		elems[next[color[e]]++] = e;
-	NB_CUDA(nbgpu::dmalloc(&m->d_color_elems, std::max<size_t>(1, m->N_elems) * sizeof(uint32_t)));
-	NB_CUDA(cudaMemcpy(m->d_color_elems, elems.data(), (size_t)m->N_elems * sizeof(uint32_t),
-			   cudaMemcpyHostToDevice));
+	for (uint32_t k = 0; k < n_colors; k++)
+		m->color_ptr[k + 1] = m->color_ptr[k] + h_cnt[2 + k];
+	unsigned int h_next[64] = {0};
+	for (uint32_t k = 0; k < n_colors; k++)
+		h_next[k] = m->color_ptr[k];
+	e = nbgpu::dmalloc(&m->d_color_elems, std::max<size_t>(1, m->N_elems) * sizeof(uint32_t));
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d_cnt + 2, h_next, 64 * sizeof(unsigned int), cudaMemcpyHostToDevice, c.stream);
+	if (e == cudaSuccess) {
+		color_scatter_kernel<<<grid, 256, 0, c.stream>>>(m->N_elems, d_color, d_cnt + 2, m->d_color_elems);
+		c.launches++;
+		e = cudaStreamSynchronize(c.stream);
+	}
+	if (e != cudaSuccess) {
+		set_error("colouring: %s", cudaGetErrorString(e));
+		return done(NBGPU_ERR_CUDA);
+	}
 	m->n_colors = n_colors;
-	return NBGPU_OK;
+	m->d_color_block = d_color_block;
+	m->d_color = d_color;
+	return done(NBGPU_OK);
 }
 
 template <int NPE, int NGP>
@@ -847,7 +955,6 @@ int nbgpu_mesh_create(uint32_t N_nod, const double *nod, uint32_t N_elems, uint3
 	m->N_nod = N_nod;
 	m->N_elems = N_elems;
 	m->npe = npe;
-	m->h_adj.assign(adj, adj + (size_t)npe * N_elems);
 	// elements around each node, ascending element id (counting sort)
 	std::vector<uint32_t> ptr((size_t)N_nod + 1, 0), n2e((size_t)npe * N_elems);
 	for (size_t k = 0; k < (size_t)npe * N_elems; k++)
@@ -922,8 +1029,21 @@ int nbgpu_mesh_destroy(nbgpu_mesh_t *m)
 		nbgpu::dfree(m->d_enabled);
 		nbgpu::dfree(m->d_scale);
 		nbgpu::dfree(m->d_color_elems);
+		nbgpu::dfree(m->d_color_block);
 	}
 	delete m;
+	return NBGPU_OK;
+}
+
+int nbgpu_mesh_coloring(nbgpu_mesh_t *m, uint32_t *n_colors, uint8_t *colors)
+{
+	NB_INIT();
+	NB_ARG(m != nullptr);
+	NB_TRY(build_coloring(m));
+	if (n_colors)
+		*n_colors = m->n_colors;
+	if (colors && m->N_elems)
+		NB_CUDA(cudaMemcpy(colors, m->d_color, m->N_elems, cudaMemcpyDeviceToHost));
 	return NBGPU_OK;
 }
 

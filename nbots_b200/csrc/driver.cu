@@ -240,26 +240,34 @@ int nbgpu_fem_session_create(const nbgpu_mesh_desc_t *md, const nbgpu_elem_table
 	S->ap.mode = assembly_mode;
 	S->n_neu = n_neu;
 
-	// (1) graph + sparsity pattern (static_elasticity2D.c:45-50)
+	// (1) mesh on the device, then graph + sparsity pattern (static_elasticity2D.c:45-50): built on the device
+	// straight into the SELL arrays when the pattern qualifies (pattern_dev.cu), else on the host (pattern.cu)
 	double t0 = now_ms();
-	std::vector<uint32_t> rows_size(S->N), cols;
-	if (st == NBGPU_OK)
-		st = nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
-					     rows_size.data(), nullptr, &S->nnz);
-	if (st == NBGPU_OK) {
-		cols.resize(S->nnz);
-		st = nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
-					     rows_size.data(), cols.data(), &S->nnz);
-	}
-	S->ms_pattern = now_ms() - t0;
-
-	// (2) device objects
-	t0 = now_ms();
-	const size_t n_strain = (size_t)3 * S->n_gp * md->N_elems;
-	if (st == NBGPU_OK)
-		st = nbgpu_matrix_create_from_csr(S->N, rows_size.data(), cols.data(), nullptr, &S->K);
 	if (st == NBGPU_OK)
 		st = nbgpu_mesh_create(md->N_nod, md->nod, md->N_elems, md->nodes_per_elem, md->adj, &S->mesh);
+	S->ms_upload = now_ms() - t0;
+	t0 = now_ms();
+	if (st == NBGPU_OK)
+		st = nbgpu_matrix_create_from_mesh(S->mesh, md->N_edg, md->edg, &S->K);
+	if (st == NBGPU_OK && !S->K) {
+		std::vector<uint32_t> rows_size(S->N), cols;
+		st = nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
+					     rows_size.data(), nullptr, &S->nnz);
+		if (st == NBGPU_OK) {
+			cols.resize(S->nnz);
+			st = nbgpu_pattern_from_mesh(md->N_nod, md->N_elems, md->nodes_per_elem, md->adj, md->N_edg, md->edg, 2,
+						     rows_size.data(), cols.data(), &S->nnz);
+		}
+		if (st == NBGPU_OK)
+			st = nbgpu_matrix_create_from_csr(S->N, rows_size.data(), cols.data(), nullptr, &S->K);
+	}
+	if (st == NBGPU_OK)
+		st = nbgpu_matrix_info(S->K, nullptr, &S->nnz, nullptr, nullptr);
+	S->ms_pattern = now_ms() - t0;
+
+	// (2) the other device objects
+	t0 = now_ms();
+	const size_t n_strain = (size_t)3 * S->n_gp * md->N_elems;
 	if (st == NBGPU_OK)
 		st = nbgpu_malloc((void **)&S->d_vec, (2 * (size_t)S->N + n_strain) * sizeof(double));
 	if (st == NBGPU_OK && n_neu) {
@@ -279,7 +287,7 @@ int nbgpu_fem_session_create(const nbgpu_mesh_desc_t *md, const nbgpu_elem_table
 		S->d_strain = S->d_vec + 2 * (size_t)S->N;
 		st = nbgpu_sync();
 	}
-	S->ms_upload = now_ms() - t0;
+	S->ms_upload += now_ms() - t0;
 	if (st != NBGPU_OK) {
 		nbgpu_fem_session_destroy(S);
 		return st;

@@ -422,6 +422,7 @@ int build_layout(nbgpu_matrix_t *A, uint32_t N, const uint32_t *rows_size)
 int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 {
 	Context &c = ctx();
+	NB_TRY(ensure_host_pattern(A));
 	DeviceTemp rp, bad;
 	NB_TRY(rp.alloc(A->h_row_ptr.size() * sizeof(uint64_t)));
 	NB_TRY(bad.alloc(sizeof(int)));
@@ -480,6 +481,7 @@ int convert_in(nbgpu_matrix_t *A, const uint32_t *d_cols, const double *d_vals)
 int convert_out(const nbgpu_matrix_t *A, uint32_t *d_cols, double *d_vals)
 {
 	Context &c = ctx();
+	NB_TRY(ensure_host_pattern(const_cast<nbgpu_matrix_t *>(A)));
 	DeviceTemp rp;
 	NB_TRY(rp.alloc(A->h_row_ptr.size() * sizeof(uint64_t)));
 	NB_CUDA(cudaMemcpyAsync(rp.p, A->h_row_ptr.data(), A->h_row_ptr.size() * sizeof(uint64_t),
@@ -497,6 +499,23 @@ int convert_out(const nbgpu_matrix_t *A, uint32_t *d_cols, double *d_vals)
 }  // namespace
 
 namespace nbgpu {
+
+int ensure_host_pattern(nbgpu_matrix_s *A)
+{
+	if (!A->d_node_counts || A->h_row_ptr.size() == (size_t)A->N + 1)
+		return NBGPU_OK;
+	std::vector<uint32_t> counts(A->N / 2);
+	NB_CUDA(cudaStreamSynchronize(ctx().stream));
+	NB_CUDA(cudaMemcpy(counts.data(), A->d_node_counts, counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	A->h_rows_size.resize(A->N);
+	A->h_row_ptr.resize((size_t)A->N + 1);
+	A->h_row_ptr[0] = 0;
+	for (uint32_t i = 0; i < A->N; i++) {
+		A->h_rows_size[i] = 2 * counts[i >> 1];
+		A->h_row_ptr[i + 1] = A->h_row_ptr[i] + A->h_rows_size[i];
+	}
+	return NBGPU_OK;
+}
 
 // Host vector -> device through the pinned staging pair (threads pack, DMA runs from pinned memory):
 // a pageable cudaMemcpy of the solver's 8 MB vectors runs at 6 GB/s, this at PCIe speed.
@@ -566,6 +585,7 @@ int nbgpu_matrix_destroy(nbgpu_matrix_t *A)
 		nbgpu::dfree(A->d_idx16);
 		nbgpu::dfree(A->d_perm);
 		nbgpu::dfree(A->d_inv_perm);
+		nbgpu::dfree(A->d_node_counts);
 	}
 	delete A;
 	return NBGPU_OK;
@@ -705,6 +725,7 @@ int nbgpu_matrix_set_values_rows(nbgpu_matrix_t *A, double *const *rows_values)
 {
 	NB_INIT();
 	NB_ARG(A != nullptr && rows_values != nullptr);
+	NB_TRY(ensure_host_pattern(A));
 	DeviceTemp dv;
 	NB_TRY(dv.alloc(A->nnz * sizeof(double)));
 	NB_TRY(upload_rows<double>((double *)dv.p, rows_values, A->h_row_ptr));
@@ -739,6 +760,7 @@ int nbgpu_matrix_get_pattern_csr(const nbgpu_matrix_t *A, uint32_t *rows_size, u
 {
 	NB_INIT();
 	NB_ARG(A != nullptr);
+	NB_TRY(ensure_host_pattern(const_cast<nbgpu_matrix_t *>(A)));
 	if (rows_size)
 		memcpy(rows_size, A->h_rows_size.data(), (size_t)A->N * sizeof(uint32_t));
 	if (cols) {

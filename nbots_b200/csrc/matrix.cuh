@@ -59,6 +59,9 @@ struct nbgpu_matrix_s {
 	}
 	std::vector<uint32_t> h_rows_size;    // host copy of the pattern's row lengths
 	std::vector<uint64_t> h_row_ptr;      // CSR offsets (host), for value import/export
+	// pattern built on the device (pattern_dev.cu): entries per node row / 2; the two host vectors above
+	// are then filled on first use (ensure_host_pattern)
+	uint32_t *d_node_counts = nullptr;
 };
 
 namespace nbgpu {
@@ -74,6 +77,9 @@ auto by_layout(int layout, F f)
 	default: return f(std::integral_constant<int, 3>{});
 	}
 }
+
+// host mirror of the pattern (rows_size, row_ptr) of a matrix whose pattern was built on the device
+int ensure_host_pattern(nbgpu_matrix_s *A);
 
 // entry index of (row, j) in the SELL arrays
 __host__ __device__ __forceinline__ size_t sell_index(const uint32_t *slice_off,

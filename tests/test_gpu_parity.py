@@ -392,6 +392,82 @@ def test_gp_to_nodes_components_and_distortion(nbgpu_lib, kind):
     assert bad.gp_to_nodes(1, d_gp, d_n) == 1 == port.gp_to_nodes(m, 1, d_gp.to_host())[0]
 
 
+# ----------------------------------------------------- pattern + colouring on the device --
+
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_device_pattern_and_colouring(nbgpu_lib, name):
+    """the pattern built on the device from the device mesh (nbgpu_matrix_create_from_mesh) is the
+    reference's (nb_mesh2D_load_graph + nb_sparse_create) bit for bit, assembly into it gives the reference's K and
+    F; the device-built element colouring is a proper colouring and feeds the COLOR schedule."""
+    g = golden(name)
+    m = mesh_of(g)
+    mesh = api.Mesh(m)
+    K = mesh.create_matrix()
+    if K is not None:
+        assert (K.N, K.nnz) == (g["rows_size"].size, g["cols"].size) and K.blocked
+        rs, cols = K.pattern_csr()
+        assert np.array_equal(rs, g["rows_size"]) and np.array_equal(cols, g["cols"])
+        d_F = api.DeviceBuffer.zeros(K.N)
+        en = g["enabled"] if "enabled" in g.files else None
+        st, _ = mesh.assemble(K, d_F, float(g["E"]), float(g["nu"]), density=float(g["density"]),
+                              self_weight=bool(g["self_weight"]), gravity=tuple(g["gravity"]),
+                              analysis=int(g["analysis"]), thickness=float(g["thickness"]), enabled=en)
+        assert st == 0 and np.array_equal(K.values_csr(), g["K_pre"]) and np.array_equal(d_F.to_host(), g["F_pre"])
+        x = g["x"]
+        assert np.array_equal(K.spmv_host(x), port.Csr(g["rows_size"], g["cols"], g["K_pre"]).spmv(x))
+    # (None: the natural order pads more than 5 % -- ragged triangle meshes, tiny grids where the short boundary
+    # rows weigh in -- so the mesh goes to the host builder and its sigma-sorted layout, tested above)
+    n_colors, colors = mesh.coloring()
+    assert 1 <= n_colors <= 64 and colors.max() == n_colors - 1
+    adj = m.adj.reshape(-1, m.npe)
+    for c in range(n_colors):                      # no two elements of a colour share a node
+        nodes = adj[colors == c].ravel()
+        assert np.unique(nodes).size == nodes.size
+    n2, colors2 = api.Mesh(m).coloring()           # deterministic
+    assert n2 == n_colors and np.array_equal(colors, colors2)
+
+
+@pytest.mark.parametrize("kind,nx,ny", [(1, 300, 150), (0, 257, 93)])
+def test_device_pattern_on_structured_meshes(nbgpu_lib, kind, nx, ny):
+    """Meshes with (nearly) uniform rows take the device path: pattern, layout flags, K and F equal to the host
+    builder's / the port's, bit for bit."""
+    m = meshgen.structured_mesh(nx, ny, 2.0, 1.0, kind=kind)
+    mesh = api.Mesh(m)
+    K = mesh.create_matrix()
+    assert K is not None and K.blocked and K.idx16 and K.uniform_width == K.max_width and K.sigma == 1
+    ors, ocols = port.pattern_from_mesh(m)
+    rs, cols = K.pattern_csr()
+    assert np.array_equal(rs, ors) and np.array_equal(cols, ocols)
+    H = api.Matrix.from_csr(ors, ocols)            # host path: same layout decisions
+    assert (H.stored, H.max_width, H.uniform_width, H.blocked, H.idx16) == \
+        (K.stored, K.max_width, K.uniform_width, K.blocked, K.idx16)
+    d_F = api.DeviceBuffer.zeros(K.N)
+    st, _ = mesh.assemble(K, d_F, 3.0, 0.25, density=2.0, self_weight=True, gravity=(0.5, -9.0), thickness=0.3)
+    P = port.Csr(ors, ocols)
+    pst, F = port.assemble(P, m, 3.0, 0.25, density=2.0, self_weight=True, gravity=(0.5, -9.0), thickness=0.3)
+    assert st == pst == 0 and np.array_equal(K.values_csr(), P.vals) and np.array_equal(d_F.to_host(), F)
+    x = meshgen.uniform_rhs(K.N, seed=3)
+    assert np.array_equal(K.spmv_host(x), P.spmv(x))
+    d_b = api.DeviceBuffer.from_host(x); d_x = api.DeviceBuffer.zeros(K.N)
+    K.apply_dirichlet(d_b, np.arange(0, 2 * (nx + 1), dtype=np.uint32), np.zeros(2 * (nx + 1)))
+    st, it, res = K.pcg_jacobi(d_b, d_x, max_iter=40, tol=0.0)          # the solver runs on the device-built layout
+    assert (st, it) == (1, 40)
+
+
+def test_device_pattern_declines_what_it_cannot_represent(nbgpu_lib):
+    """An edge that is no element side is part of the reference's graph but not of the element graph: the device
+    builder hands the mesh back to the host builder instead of producing another pattern."""
+    m = meshgen.structured_mesh(12, 7, 2.0, 1.0, kind=1)
+    mesh = api.Mesh(m)
+    assert mesh.create_matrix() is not None
+    m2 = meshgen.structured_mesh(12, 7, 2.0, 1.0, kind=1)
+    m2.edg = np.concatenate([m2.edg, np.array([0, 50], dtype=np.uint32)])
+    assert api.Mesh(m2).create_matrix() is None
+    rs, cols = api.pattern_from_mesh(m2)            # the host builder keeps the extra link
+    ors, ocols = port.pattern_from_mesh(m2)
+    assert np.array_equal(rs, ors) and np.array_equal(cols, ocols)
+
+
 # ------------------------------------------------------------------------ driver --
 
 class _Desc(C.Structure):
