@@ -457,10 +457,10 @@ def test_device_pattern_on_structured_meshes(nbgpu_lib, kind, nx, ny):
 def test_device_pattern_declines_what_it_cannot_represent(nbgpu_lib):
     """An edge that is no element side is part of the reference's graph but not of the element graph: the device
     builder hands the mesh back to the host builder instead of producing another pattern."""
-    m = meshgen.structured_mesh(12, 7, 2.0, 1.0, kind=1)
+    m = meshgen.structured_mesh(120, 70, 2.0, 1.0, kind=1)
     mesh = api.Mesh(m)
     assert mesh.create_matrix() is not None
-    m2 = meshgen.structured_mesh(12, 7, 2.0, 1.0, kind=1)
+    m2 = meshgen.structured_mesh(120, 70, 2.0, 1.0, kind=1)
     m2.edg = np.concatenate([m2.edg, np.array([0, 50], dtype=np.uint32)])
     assert api.Mesh(m2).create_matrix() is None
     rs, cols = api.pattern_from_mesh(m2)            # the host builder keeps the extra link
