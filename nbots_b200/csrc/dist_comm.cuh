@@ -316,7 +316,7 @@ struct PeerComm {
 		return collect_slots<NV>(mine, world, timeout_ns, seq, v);
 	}
 	template <int NV>
-	__device__ __noinline__ bool all_reduce(double (&v)[NV], unsigned long long seq) const
+	__device__ __forceinline__ bool all_reduce(double (&v)[NV], unsigned long long seq) const
 	{
 		post<NV>(v, seq);
 		return collect<NV>(seq, v);

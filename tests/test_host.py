@@ -165,12 +165,14 @@ def test_streamed_kernels_fit_two_ctas_per_sm():
     found = 0
     for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
         name, reg, stack = m.group(1), int(m.group(2)), int(m.group(3))
-        if any(k in name for k in ("spmv_stream_kernel", "init_stream_kernel", "dist_spmv_kernel",
-                                    "dist_init_kernel", "dist_plain_spmv_kernel")):
+        if any(k in name for k in ("spmv_stream_kernel", "init_stream_kernel", "fspmv_kernel", "dist_plain_spmv_kernel")):
             found += 1
-            assert stack == 0, (name, "spills")
+            # the row-partitioned variants pass a 2-3 double array to the out-of-line exchange (collect_slots):
+            # that argument lives in a 16-24 byte frame; anything else in the frame would be a spill
+            assert stack == 0 or ("PeerComm" in name and stack <= 24), (name, "spills")
             assert reg <= 96, (name, reg)
-    assert found >= 20          # 4 layouts x (spmv, krylov spmv, 2 x init) + the distributed kernels
+    # 4 layouts x (spmv, distributed spmv) + 4 layouts x 2 exchange policies x (classic K1, 2 x fused K1, 2 x init)
+    assert found >= 48
     sass = subprocess.run([cuobjdump, "-sass", "-fun", "nbgpu::spmv_stream_kernel<(int)3>", capi.LIB_PATH],
                           capture_output=True, text=True).stdout
     if "UBLKCP" not in sass:    # older cuobjdump builds want the mangled name
