@@ -537,6 +537,19 @@ int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *mesh, int rank, int world,
 			  const double gravity[2], double thickness,
 			  void *ipc_handle_out, nbgpu_dist_fem_t **out);
 int nbgpu_dist_fem_destroy(nbgpu_dist_fem_t *fem);
+/* Host logic only (no device): the partition plan nbgpu_dist_fem_create derives
+ * from the mesh by itself -- halo list, column-space layout, local column ids of
+ * the owned rows AND the send lists (no exchange of lists between the ranks).
+ * rows_size may be NULL or [2 * owned nodes]; read the rest back with
+ * nbgpu_dist_plan_info / _layout / _halo_ids / _local_cols / _sends. */
+int nbgpu_dist_plan_from_mesh(const nbgpu_mesh_desc_t *mesh, int rank, int world,
+			      const uint32_t *node_starts, uint32_t *rows_size,
+			      nbgpu_dist_plan_t **out);
+/* send side of a plan: counts per destination, the global rows sent (grouped by
+ * destination; NULL to get the counts first), where each block lands in the
+ * destination's column space */
+int nbgpu_dist_plan_sends(const nbgpu_dist_plan_t *plan, uint32_t *send_counts,
+			  uint32_t *send_global, uint32_t *dst_offsets);
 int nbgpu_dist_fem_info(const nbgpu_dist_fem_t *fem, uint32_t *N_loc,
 			uint64_t *nnz_loc, uint32_t *n_halo, uint32_t *n_elems_loc,
 			uint64_t *ext_len, double *ms_setup);

@@ -159,6 +159,8 @@ SIGNATURES = {
                                         u32p, f64p, C.c_uint32, u32p, f64p, C.c_int, f64p, C.c_double, C.c_void_p,
                                         vpp]),
     "nbgpu_dist_fem_destroy": (C.c_int, [C.c_void_p]),
+    "nbgpu_dist_plan_from_mesh": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, u32p, vpp]),
+    "nbgpu_dist_plan_sends": (C.c_int, [C.c_void_p, u32p, u32p, u32p]),
     "nbgpu_dist_fem_info": (C.c_int, [C.c_void_p, u32p, u64p, u32p, u32p, u64p, f64p]),
     "nbgpu_dist_fem_connect": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
     "nbgpu_dist_fem_connect_local": (C.c_int, [C.c_void_p, vpp, C.POINTER(C.c_int)]),

@@ -109,22 +109,29 @@ int nbgpu_dist_fem_destroy(nbgpu_dist_fem_t *S)
 	return NBGPU_OK;
 }
 
-int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, const uint32_t *node_starts,
-			  const nbgpu_elem_tables_t *tables, const double D[4], double density, uint32_t n_neu,
-			  const uint32_t *neu_dof, const double *neu_add, uint32_t n_dir, const uint32_t *dir_dof,
-			  const double *dir_val, int self_weight, const double gravity[2], double thickness,
-			  void *ipc_handle_out, nbgpu_dist_fem_t **out)
+}  // extern "C"
+
+namespace {
+
+// Host part of nbgpu_dist_fem_create: this rank's sub-mesh (elements, ghost nodes, column-space numbering),
+// the partition plan with its send lists, and the pattern of the owned rows.  No device is touched.
+struct SubMesh {
+	std::vector<uint32_t> adj_loc;     // [npe n_el] column-space node ids
+	std::vector<double> nod_loc;       // [2 n_sub_nodes]
+	std::vector<uint32_t> rows_size;   // [N_loc]
+	uint32_t n_sub_nodes = 0;
+};
+
+int plan_sub_mesh(const nbgpu_mesh_desc_t *md, int rank, int world, const uint32_t *node_starts, nbgpu_dist_fem_t *S,
+		  SubMesh *M)
 {
-	NB_INIT();
-	NB_ARG(md != nullptr && out != nullptr && D != nullptr && node_starts != nullptr);
+	NB_ARG(md != nullptr && node_starts != nullptr);
 	NB_ARG(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world);
 	NB_ARG(md->nodes_per_elem == 3 || md->nodes_per_elem == 4);
 	NB_ARG(node_starts[0] == 0 && node_starts[world] == md->N_nod);
 	for (int r = 0; r < world; r++)
 		NB_ARG(node_starts[r] <= node_starts[r + 1]);
-	const double t0 = now_ms();
 	const uint32_t npe = md->nodes_per_elem, n0 = node_starts[rank], n1 = node_starts[rank + 1];
-	nbgpu_dist_fem_t *S = new nbgpu_dist_fem_t();
 	S->rank = rank;
 	S->world = world;
 	S->n0 = n0;
@@ -143,7 +150,6 @@ int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, cons
 			hi = std::max(hi, v[i]);
 		}
 		if (hi >= md->N_nod) {
-			delete S;
 			set_error("element %u references node %u >= N_nod", e, hi);
 			return NBGPU_ERR_ARG;
 		}
@@ -186,10 +192,8 @@ int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, cons
 	P->n_halo = 2 * (uint32_t)G.size();
 	P->n_lo = 2 * n_lo_nodes;
 	P->n_hi = P->n_halo - P->n_lo;
-	if (nbgpu_dist_ext_layout(P->n_lo, P->N_loc, P->n_hi, &P->off_own, &P->off_up, &P->ext_len) != NBGPU_OK) {
-		nbgpu_dist_fem_destroy(S);
+	if (nbgpu_dist_ext_layout(P->n_lo, P->N_loc, P->n_hi, &P->off_own, &P->off_up, &P->ext_len) != NBGPU_OK)
 		return NBGPU_ERR_ARG;
-	}
 	P->halo_global.resize(P->n_halo);
 	P->recv_counts.assign(world, 0);
 	for (size_t i = 0; i < G.size(); i++) {
@@ -234,8 +238,11 @@ int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, cons
 		return h < n_lo_nodes ? h : up_node0 + (h - n_lo_nodes);
 	};
 	const uint32_t n_el = (uint32_t)S->elems.size();
-	std::vector<uint32_t> adj_loc((size_t)npe * n_el);
-	std::vector<double> nod_loc(2 * (size_t)n_sub_nodes, 0.0);
+	std::vector<uint32_t> &adj_loc = M->adj_loc;
+	std::vector<double> &nod_loc = M->nod_loc;
+	adj_loc.assign((size_t)npe * n_el, 0);
+	nod_loc.assign(2 * (size_t)n_sub_nodes, 0.0);
+	M->n_sub_nodes = n_sub_nodes;
 #pragma omp parallel for schedule(static)
 	for (int64_t t = 0; t < (int64_t)n_el; t++) {
 		const uint32_t *v = md->adj + (size_t)S->elems[t] * npe;
@@ -275,7 +282,8 @@ int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, cons
 					e_of[next[l - own_node0]++] = t;
 			}
 	}
-	std::vector<uint32_t> rows_size((size_t)P->N_loc);
+	std::vector<uint32_t> &rows_size = M->rows_size;
+	rows_size.assign((size_t)P->N_loc, 0);
 	std::vector<uint64_t> nb_ptr((size_t)n_own + 1, 0);
 	// two passes: count, then fill
 	auto neighbours = [&](uint32_t i, uint32_t *buf) -> uint32_t {
@@ -319,6 +327,47 @@ int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, cons
 		}
 	}
 	plan_visit_order(P, rows_size.data());
+
+	return NBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, const uint32_t *node_starts,
+			  const nbgpu_elem_tables_t *tables, const double D[4], double density, uint32_t n_neu,
+			  const uint32_t *neu_dof, const double *neu_add, uint32_t n_dir, const uint32_t *dir_dof,
+			  const double *dir_val, int self_weight, const double gravity[2], double thickness,
+			  void *ipc_handle_out, nbgpu_dist_fem_t **out)
+{
+	NB_INIT();
+	NB_ARG(md != nullptr && out != nullptr && D != nullptr && node_starts != nullptr);
+	const double t0 = now_ms();
+	nbgpu_dist_fem_t *S = new nbgpu_dist_fem_t();
+	SubMesh sub;
+	{
+		const int pst = plan_sub_mesh(md, rank, world, node_starts, S, &sub);
+		if (pst != NBGPU_OK) {
+			nbgpu_dist_fem_destroy(S);
+			return pst;
+		}
+	}
+	nbgpu_dist_plan_t *P = S->plan;
+	const uint32_t npe = S->npe, n0 = S->n0, n1 = S->n1, n_lo_nodes = S->n_lo_nodes;
+	const std::vector<uint32_t> &G = S->ghosts;
+	const uint32_t own_node0 = P->off_own / 2, up_node0 = P->off_up / 2, n_sub_nodes = sub.n_sub_nodes;
+	const uint32_t n_el = (uint32_t)S->elems.size();
+	std::vector<uint32_t> &adj_loc = sub.adj_loc, &rows_size = sub.rows_size;
+	std::vector<double> &nod_loc = sub.nod_loc;
+	auto local_node = [&](uint32_t g) -> uint32_t {
+		if (g >= n0 && g < n1)
+			return own_node0 + (g - n0);
+		const uint32_t h = (uint32_t)(std::lower_bound(G.begin(), G.end(), g) - G.begin());
+		if (h >= G.size() || G[h] != g)
+			return 0xFFFFFFFFu;
+		return h < n_lo_nodes ? h : up_node0 + (h - n_lo_nodes);
+	};
 
 	// ---- device objects
 	int st = nbgpu_matrix_create_local(P->N_loc, P->ext_len, P->off_own, rows_size.data(), P->cols_local.data(),
@@ -401,6 +450,44 @@ int nbgpu_dist_fem_create(const nbgpu_mesh_desc_t *md, int rank, int world, cons
 	S->ap.mode = NBGPU_ASSEMBLY_GATHER;
 	S->ms_setup = now_ms() - t0;
 	*out = S;
+	return NBGPU_OK;
+}
+
+/* Host logic only (no device): the partition plan nbgpu_dist_fem_create derives from the mesh -- halo list,
+ * column-space layout, send lists, local column ids of the owned rows (nbgpu_dist_plan_* read it back).
+ * rows_size may be NULL or [2 * owned nodes]. */
+int nbgpu_dist_plan_from_mesh(const nbgpu_mesh_desc_t *md, int rank, int world, const uint32_t *node_starts,
+			      uint32_t *rows_size, nbgpu_dist_plan_t **out)
+{
+	NB_ARG(out != nullptr);
+	nbgpu_dist_fem_t S;
+	SubMesh sub;
+	const int st = plan_sub_mesh(md, rank, world, node_starts, &S, &sub);
+	if (st != NBGPU_OK) {
+		nbgpu_dist_plan_destroy(S.plan);
+		return st;
+	}
+	if (rows_size)
+		memcpy(rows_size, sub.rows_size.data(), sub.rows_size.size() * sizeof(uint32_t));
+	*out = S.plan;
+	S.plan = nullptr;
+	return NBGPU_OK;
+}
+
+/* the plan's send side: counts per destination, the global rows sent (grouped by destination) and where each block
+ * lands in the destination's column space; send_global may be NULL to get the counts first */
+int nbgpu_dist_plan_sends(const nbgpu_dist_plan_t *P, uint32_t *send_counts, uint32_t *send_global, uint32_t *dst_offsets)
+{
+	NB_ARG(P != nullptr && P->have_sends);
+	for (int r = 0; r < P->world; r++) {
+		if (send_counts)
+			send_counts[r] = P->send_ptr[r + 1] - P->send_ptr[r];
+		if (dst_offsets)
+			dst_offsets[r] = P->dst_offset[r];
+	}
+	if (send_global)
+		for (size_t j = 0; j < P->send_local.size(); j++)
+			send_global[j] = P->send_local[j] + P->row_starts[P->rank];
 	return NBGPU_OK;
 }
 

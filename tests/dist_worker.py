@@ -168,6 +168,55 @@ def run_gpu(rank, world):
     dc.close()
 
 
+def run_cpu_fem(rank, world):
+    """Host logic of the distributed FEM path, no GPU: the plan nbgpu_dist_plan_from_mesh derives from the mesh alone
+    (ghost nodes, column space, local columns, SEND lists) against the plan built from the pattern of this rank's
+    rows plus the exchange of halo lists between the ranks (nbgpu_dist_plan_create + set_sends over gloo), on the
+    reference's triangle meshes cut into node ranges and on the quad fixtures cut into slabs."""
+    import ctypes as C
+    from nbots_b200 import capi
+    from util import FEM_CASES, mesh_of
+    L = capi.lib()
+    gather = gather_obj_fn(world)
+    u32p = capi.u32p
+    for name in FEM_CASES:
+        g = golden(name)
+        m = mesh_of(g)
+        node_starts = np.zeros(world + 1, dtype=np.uint32)
+        capi.check(L.nbgpu_partition_nodes(m.n_nod, world, 65 if name == "quad_cantilever_64x16" else 1,
+                                           node_starts.ctypes.data_as(u32p)))
+        n0, n1 = int(node_starts[rank]), int(node_starts[rank + 1])
+        r0, r1 = 2 * n0, 2 * n1
+        desc = capi.MeshDesc.of(m)
+        rs_f = np.zeros(r1 - r0, dtype=np.uint32)
+        ph = C.c_void_p()
+        capi.check(L.nbgpu_dist_plan_from_mesh(C.byref(desc), rank, world, node_starts.ctypes.data_as(u32p),
+                                               rs_f.ctypes.data_as(u32p), C.byref(ph)))
+        F = multigpu.PlanView(ph.value, world)
+        cl_f = np.zeros(max(1, F.nnz), dtype=np.uint32)
+        capi.check(L.nbgpu_dist_plan_local_cols(ph.value, cl_f.ctypes.data_as(u32p)))
+        sc = np.zeros(world, dtype=np.uint32); so = np.zeros(world, dtype=np.uint32)
+        capi.check(L.nbgpu_dist_plan_sends(ph.value, sc.ctypes.data_as(u32p), None, so.ctypes.data_as(u32p)))
+        sg = np.zeros(max(1, int(sc.sum())), dtype=np.uint32)
+        capi.check(L.nbgpu_dist_plan_sends(ph.value, sc.ctypes.data_as(u32p), sg.ctypes.data_as(u32p), so.ctypes.data_as(u32p)))
+        # the same through the pattern of this rank's rows and the list exchange
+        rs, cols = g["rows_size"], g["cols"]
+        rp = port.row_ptr_of(rs).astype(np.int64)
+        dc = multigpu.DistContext(rank, world, 2 * node_starts, rs[r0:r1], cols[rp[r0]:rp[r1]], None, gather)
+        assert np.array_equal(rs_f, rs[r0:r1]), name
+        assert (F.N_loc, F.n_halo, F.nnz) == (dc.N_loc, dc.n_halo, int(rp[r1] - rp[r0])), name
+        assert (F.n_lo, F.off_own, F.off_up, F.ext_len) == (dc.n_lo, dc.off_own, dc.off_up, dc.ext_len), name
+        assert np.array_equal(F.halo_global, dc.halo_global) and np.array_equal(F.recv_counts, dc.recv_counts), name
+        assert np.array_equal(cl_f[:F.nnz], dc.cols_local), name
+        assert np.array_equal(sc, dc.send_counts) and np.array_equal(sg[:int(sc.sum())], dc.send_global), name
+        live = sc > 0
+        assert np.array_equal(so[live], dc.dst_offsets[live]), name
+        L.nbgpu_dist_plan_destroy(ph.value)
+        dc.close()
+    if rank == 0:
+        print("DIST_OK cpu-fem")
+
+
 def run_gpu_fem(rank, world):
     """nbgpu_dist_fem_*: device-side assembly of the rank-local rows (structured slabs AND the reference's
     unstructured triangle meshes cut into contiguous node ranges), bit for bit the reference's rows; then the
@@ -225,7 +274,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
     try:
-        {"cpu": run_cpu, "gpu": run_gpu, "gpu-fem": run_gpu_fem}[mode](rank, world)
+        {"cpu": run_cpu, "cpu-fem": run_cpu_fem, "gpu": run_gpu, "gpu-fem": run_gpu_fem}[mode](rank, world)
     finally:
         dist.destroy_process_group()
 

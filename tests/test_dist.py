@@ -24,6 +24,12 @@ def test_partition_plan_and_exchange_on_cpu(world):
     assert out.returncode == 0 and "DIST_OK cpu" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_fem_plan_from_mesh_on_cpu(world):
+    out = launch("cpu-fem", world, 29650 + world)
+    assert out.returncode == 0 and "DIST_OK cpu-fem" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
 def test_distributed_solve_on_gpus(nbgpu_lib, world):
