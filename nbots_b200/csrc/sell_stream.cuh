@@ -279,12 +279,14 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 	uint32_t row_ahead = 0;
 	if (A.perm && first < A.n_slices)
 		row_ahead = __ldg(A.perm + (size_t)slice_of(first) * kSliceRows + lane);
+	// ring position of visit n (n % stages) and its mbarrier phase ((n / stages) & 1), kept incrementally:
+	// a division by the run-time ring depth per slice is ~25 instructions of a ~440-instruction slice
+	uint32_t st = 0, parity = 0;
 	for (uint64_t s64 = first; s64 < A.n_slices; s64 += total_warps, n++) {
 		const uint32_t s = slice_of(s64);
 		const uint32_t row = A.perm ? row_ahead : s * kSliceRows + lane;
 		if (A.perm && s64 + total_warps < A.n_slices)
 			row_ahead = __ldg(A.perm + (size_t)slice_of(s64 + total_warps) * kSliceRows + lane);
-		const uint32_t st = n % cfg.stages, parity = (n / cfg.stages) & 1u;
 		if (!late_done && s64 >= A.late_from) {
 			late_done = true;
 			if (!late()) {
@@ -494,6 +496,10 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			slice_work(std::true_type{});
 		else
 			slice_work(std::false_type{});
+		if (++st == cfg.stages) {
+			st = 0;
+			parity ^= 1u;
+		}
 	}
 }
 
