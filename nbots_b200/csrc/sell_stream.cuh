@@ -440,51 +440,72 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 				}
 			}
 		} else {
-			// one node id per 2x2 block; lanes 2k, 2k+1 (the two dofs of a node) share it
+			// one node id per 2x2 block; lanes 2k, 2k+1 (the two dofs of a node) share it.
+			// The work per block is ~45 instructions and the kernel's time follows its instruction count
+			// closely (ncu: 440 per slice, issue slots half used by 20 warps per SM), so two things are kept
+			// out of the common case:
+			//  * padding: entries are ascending, so a row is padded iff its LAST block id is the marker; a
+			//    warp vote picks the loop without any padding selects (uniform meshes: only slices with
+			//    boundary rows have padding, 0.3 % at Q1);
+			//  * x[row]: picked out of the diagonal block only when the diagonal VALUE is wanted as well
+			//    (init kernel); otherwise it is one more coalesced load issued with the gathers.
 			const uint32_t nblk = width >> 1;
 			const uint32_t my_node = crow >> 1;
-			uint32_t b0 = 0;
-			for (; b0 + kGatherBatch <= nblk; b0 += kGatherBatch) {
-				uint32_t cb[kGatherBatch];
-				double2 xb[kGatherBatch];
+			const bool padded = nblk != 0 && load_id(nblk - 1) == kPadCol;
+			const bool any_pad = __any_sync(0xffffffffu, padded);
+			if (!WANT_DIAG && row < A.N) {
+				x_row = __ldg(x + crow);   // (a plain load: dropped by the compiler where the body ignores x[row])
+				have_row = true;
+			}
+			auto blocks = [&](auto pads_tag) {
+				constexpr bool kPads = decltype(pads_tag)::value;
+				uint32_t b0 = 0;
+				for (; b0 + kGatherBatch <= nblk; b0 += kGatherBatch) {
+					uint32_t cb[kGatherBatch];
+					double2 xb[kGatherBatch];
 #pragma unroll
-				for (int u = 0; u < kGatherBatch; u++)
-					cb[u] = load_id(b0 + u);
+					for (int u = 0; u < kGatherBatch; u++)
+						cb[u] = load_id(b0 + u);
 #pragma unroll
-				for (int u = 0; u < kGatherBatch; u++)
-					xb[u] = gather2(x + 2 * (size_t)(cb[u] == kPadCol ? 0u : cb[u]));
-				__syncwarp();
+					for (int u = 0; u < kGatherBatch; u++)
+						xb[u] = gather2(x + (uint32_t)(2u * ((kPads && cb[u] == kPadCol) ? 0u : cb[u])));
+					__syncwarp();
 #pragma unroll
-				for (int u = 0; u < kGatherBatch; u++) {
-					const double v0 = sval[(2 * (b0 + u)) * kSliceRows];
-					const double v1 = sval[(2 * (b0 + u) + 1) * kSliceRows];
-					const bool pad = cb[u] == kPadCol;
-					const double t0 = __dmul_rn(v0, xb[u].x);
+					for (int u = 0; u < kGatherBatch; u++) {
+						const double v0 = sval[(2 * (b0 + u)) * kSliceRows];
+						const double v1 = sval[(2 * (b0 + u) + 1) * kSliceRows];
+						const bool pad = kPads && cb[u] == kPadCol;
+						const double t0 = __dmul_rn(v0, xb[u].x);
+						acc = pad ? acc : __dadd_rn(acc, t0);
+						const double t1 = __dmul_rn(v1, xb[u].y);
+						acc = pad ? acc : __dadd_rn(acc, t1);
+						if (WANT_DIAG && cb[u] == my_node) {
+							diag = (row & 1) ? v1 : v0;
+							x_row = (row & 1) ? xb[u].y : xb[u].x;
+							have_row = true;
+						}
+					}
+				}
+				for (; b0 < nblk; b0++) {
+					const uint32_t cb = load_id(b0);
+					const double v0 = sval[(2 * b0) * kSliceRows], v1 = sval[(2 * b0 + 1) * kSliceRows];
+					const bool pad = kPads && cb == kPadCol;
+					const double2 xb = gather2(x + (uint32_t)(2u * (pad ? 0u : cb)));
+					const double t0 = __dmul_rn(v0, xb.x);
 					acc = pad ? acc : __dadd_rn(acc, t0);
-					const double t1 = __dmul_rn(v1, xb[u].y);
+					const double t1 = __dmul_rn(v1, xb.y);
 					acc = pad ? acc : __dadd_rn(acc, t1);
-					if (cb[u] == my_node) {
+					if (WANT_DIAG && cb == my_node) {
 						diag = (row & 1) ? v1 : v0;
-						x_row = (row & 1) ? xb[u].y : xb[u].x;
+						x_row = (row & 1) ? xb.y : xb.x;
 						have_row = true;
 					}
 				}
-			}
-			for (; b0 < nblk; b0++) {
-				const uint32_t cb = load_id(b0);
-				const double v0 = sval[(2 * b0) * kSliceRows], v1 = sval[(2 * b0 + 1) * kSliceRows];
-				const double2 xb = gather2(x + 2 * (size_t)(cb == kPadCol ? 0u : cb));
-				const bool pad = cb == kPadCol;
-				const double t0 = __dmul_rn(v0, xb.x);
-				acc = pad ? acc : __dadd_rn(acc, t0);
-				const double t1 = __dmul_rn(v1, xb.y);
-				acc = pad ? acc : __dadd_rn(acc, t1);
-				if (cb == my_node) {
-					diag = (row & 1) ? v1 : v0;
-					x_row = (row & 1) ? xb.y : xb.x;
-					have_row = true;
-				}
-			}
+			};
+			if (any_pad)
+				blocks(std::true_type{});
+			else
+				blocks(std::false_type{});
 		}
 		if (!single)
 			release();
