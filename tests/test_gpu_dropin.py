@@ -153,6 +153,20 @@ OTHER_CALLERS = textwrap.dedent('''
             K.dirichlet(b, 2 * fv + a, vertex[2 * fv + a])
     st, v, it, res = K.pcg_jacobi(b, x0=vertex, max_iter=2 * nv, tol=1e-12)
     out["regularize"] = {"status": st, "vertex": v.tolist(), "iters": it}
+    # (c) the disk-packing mesher's Newton step (elements2D/mshpack.c:645-679): THREE unknowns per node
+    # (nb_sparse_create(&graph, NULL, 3): no 2x2 block structure), solver called with the previous step as initial
+    # guess, max_iter = 2 N, absolute tolerance 1e-8
+    n_adj3, adj3 = meshgen.laplacian9_graph(20)
+    H = ref.RefSparse.from_graph(n_adj3, adj3, 3)
+    rs3, cols3, _ = H.export()
+    row_of = np.repeat(np.arange(rs3.size), rs3)
+    lo, hi = np.minimum(row_of, cols3), np.maximum(row_of, cols3)
+    vals3 = -0.05 * (1.0 + ((lo * 7919 + hi * 104729) %% 97) / 97.0)          # symmetric by construction
+    vals3[row_of == cols3] = 3.0                                               # diagonally dominant: SPD
+    H.set_values(vals3)
+    b3 = meshgen.uniform_rhs(rs3.size, seed=11)
+    st, h1, it, res = H.pcg_jacobi(b3, x0=0.01 * meshgen.uniform_rhs(rs3.size, seed=12), max_iter=2 * rs3.size, tol=1e-8)
+    out["mshpack_step"] = {"status": st, "h": h1.tolist(), "iters": it}
     if WITH_SHIM:
         out["launches"] = int(capi.lib().nbgpu_launch_count())
     print("RESULT " + json.dumps(out))
@@ -163,7 +177,8 @@ OTHER_CALLERS = textwrap.dedent('''
 def test_other_krylov_callers_of_the_reference_through_the_shim(nbgpu_lib):
     """the reference's other users of the two solver entry points -- inverse power iteration
     (inv_power.c:75 Jacobi-PCG, :80 plain CG), run unmodified, and the model regulariser's solve (regularizer.c:49;
-    its system restated, see the script) -- with libnbots_b200.so interposed; results against the same calls on the CPU: bit-identical with reference-order
+    its system restated, see the script) and the disk-packing mesher's Newton step (mshpack.c:676: three unknowns
+    per node, warm start, max_iter = 2 N) -- with libnbots_b200.so interposed; results against the same calls on the CPU: bit-identical with reference-order
     dot products, within solver tolerance with the default parallel-tree reductions."""
     import json
 
@@ -186,6 +201,9 @@ def test_other_krylov_callers_of_the_reference_through_the_shim(nbgpu_lib):
     assert exact["regularize"]["vertex"] == cpu["regularize"]["vertex"]
     assert exact["regularize"]["iters"] == cpu["regularize"]["iters"]
     assert abs(tree["regularize"]["iters"] - cpu["regularize"]["iters"]) <= max(1, 0.02 * cpu["regularize"]["iters"])
+    assert exact["mshpack_step"] == cpu["mshpack_step"] and cpu["mshpack_step"]["status"] == 0
+    assert abs(tree["mshpack_step"]["iters"] - cpu["mshpack_step"]["iters"]) <= 1
+    np.testing.assert_allclose(tree["mshpack_step"]["h"], cpu["mshpack_step"]["h"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(tree["regularize"]["vertex"], cpu["regularize"]["vertex"], rtol=0, atol=1e-9)
 
 
