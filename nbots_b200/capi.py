@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("NBGPU_LIB_DIR") or os.path.join(_HERE, "lib")   # (diagnostic builds live in other dirs)
 LIB_PATH = os.path.join(LIB_DIR, "libnbgpu.so")
 SHIM_PATH = os.path.join(LIB_DIR, "libnbots_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nbgpu.h")

@@ -609,6 +609,17 @@ double *nbgpu_dist_input_vector(nbgpu_dist_t *D, const nbgpu_dist_plan_t *P)
 	return (D && P) ? D->x_ext() + P->off_own : nullptr;
 }
 
+#ifdef NB_TIMELINE
+/* diagnostic builds only: the %globaltimer stamps of the last row-partitioned solve, [512][10] */
+int nbgpu_dist_timeline(unsigned long long *out)
+{
+	NB_INIT();
+	NB_CUDA(cudaStreamSynchronize(ctx().stream));
+	NB_CUDA(cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * kTlIters * kTlSlots));
+	return NBGPU_OK;
+}
+#endif
+
 /* communication error raised by a kernel wait (0 = none) */
 int nbgpu_dist_error(nbgpu_dist_t *D)
 {

@@ -270,18 +270,21 @@ struct PeerComm {
 
 	// Called by every thread after the kernel's gate.  The boundary entries leave at the START of the
 	// kernel that consumes the vector, while the other warps already stream the matrix; the neighbours
-	// only need them for their last slices.  A push costs its warp a system-scope fence (an NVLink
-	// round trip), so it is given to the LAST warp of the LAST CTAs, 32 values each: with slices dealt
-	// round-robin those warps own one slice fewer than the first ones whenever the division leaves a rest.
+	// only need them for their last slices.  A push costs its warp ~5 us (gather, NVLink stores, a
+	// system-scope fence, the ticket), so WHICH warps push decides the kernel's tail: the CTAs of a
+	// programmatically launched grid become resident in blockIdx order as the predecessor's CTAs retire,
+	// so the FIRST CTAs start (and finish) microseconds before the last ones (timeline, 1 M dof: CTA 0 is
+	// done 4 us before the last CTA).  The push is therefore given to one warp of each of the first CTAs,
+	// 32 values each -- it sits in their slack and leaves as early as possible; on the last CTAs (round 1)
+	// it extended the kernel by 5 us per iteration.
 	__device__ __forceinline__ void push_halo(const double *v_own, int which, unsigned long long seq,
 						  unsigned int *ticket) const
 	{
 		if (total_sends == 0)
 			return;
 		const uint32_t n_push = min(gridDim.x, (total_sends + 31u) / 32u);
-		const uint32_t first_cta = gridDim.x - n_push;
-		if ((threadIdx.x >> 5) == (blockDim.x >> 5) - 1 && blockIdx.x >= first_cta)
-			push_piece(v_own, which, seq, ticket, blockIdx.x - first_cta, n_push);
+		if ((threadIdx.x >> 5) == (blockDim.x >> 5) - 1 && blockIdx.x < n_push)
+			push_piece(v_own, which, seq, ticket, blockIdx.x, n_push);
 	}
 	// (cold: kept out of line so that it costs the streaming loop no registers)
 	__device__ __noinline__ void push_piece(const double *v_own, int which, unsigned long long seq,

@@ -62,6 +62,25 @@ struct KrylovState {
 	unsigned int push_ticket;   // halo pushes (separate from the reductions' ticket: both live in K1)
 };
 
+// Optional timeline (build with EXTRA=-DNB_TIMELINE into another LIBDIR; scripts/dist_timeline.py): per-GPU
+// %globaltimer stamps at the phase boundaries of the first 512 iterations, to see where an iteration of the
+// row-partitioned solver waits.  Compiled out of the product.
+#ifdef NB_TIMELINE
+constexpr int kTlSlots = 10, kTlIters = 512;
+static __device__ unsigned long long g_timeline[kTlIters * kTlSlots];
+__device__ __forceinline__ void tl_stamp(uint32_t k, int slot)
+{
+	if (k < kTlIters) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+		g_timeline[k * kTlSlots + slot] = t;
+	}
+}
+#define NB_TL(k, slot) tl_stamp(k, slot)
+#else
+#define NB_TL(k, slot) ((void)0)
+#endif
+
 constexpr int kIterUnroll = 6;
 constexpr uint32_t kChunkIters = 32;
 
@@ -248,11 +267,18 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 			// a function of (k, state) only: the whole grid takes the same branch
 			const int failed = comm.failed();   // loaded beside the gate's state line, not behind it
 			active = iteration_gate(k, st) && !failed;
+			if (blockIdx.x == 0 && threadIdx.x == 0)
+				NB_TL(k, 0);
 			if (active)
 				comm.push_halo(p_ext + A.col_shift, 0, seq_halo, &st->push_ticket);
 			return active;
 		},
-		[&] { return comm.wait_halo(0, seq_halo); },   // only the slices that read halo columns wait
+		[&] {
+			const bool ok = comm.wait_halo(0, seq_halo);   // only the slices that read halo columns wait
+			if (blockIdx.x == 0 && threadIdx.x == 0)
+				NB_TL(k, 2);
+			return ok;
+		},
 		NoPre(),
 		[&](uint32_t row, double acc, double, double p_row, double) {
 			if (row < A.N) {
@@ -266,8 +292,12 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 		cta_store_partials<1>(dots, partials);   // K2's CTAs sum them (common.cuh)
 		return;
 	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		NB_TL(k, 9);
 	double tot[1];
 	if (grid_reduce<1>(dots, partials, &st->ticket, tot)) {
+		if (threadIdx.x == 0)
+			NB_TL(k, 1);
 		if (Comm::kDist)
 			comm.template post<1>(tot, seq_red);   // K2's CTAs collect the ranks' partials
 		else if (threadIdx.x == 0)
@@ -310,6 +340,8 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 		const uint64_t i = (uint64_t)base + (uint64_t)b * stride;
 		wv[b] = i < N ? w[i] : 0.0;
 	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		NB_TL(k, 3);
 	if (Comm::kDist) {
 		// every CTA collects the ranks' partials of K1 itself (dist_comm.cuh)
 		double t[1];
@@ -318,6 +350,8 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 				comm_abort(st);
 			return;
 		}
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			NB_TL(k, 4);
 		pw_k = t[0];
 		if (blockIdx.x == 0 && threadIdx.x == 0)
 			st->pw = pw_k;   // K3 reads it
@@ -366,6 +400,8 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 	}
 	double tot[2];
 	if (grid_reduce<2>(dots, partials, &st->ticket, tot)) {
+		if (threadIdx.x == 0)
+			NB_TL(k, 5);
 		if (!JACOBI)
 			tot[1] = tot[0];
 		if (Comm::kDist) {
@@ -408,6 +444,8 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 		const uint64_t i = (uint64_t)base + (uint64_t)b * stride;
 		qv[b] = i < N ? q[i] : 0.0;
 	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		NB_TL(k, 6);
 	if (Comm::kDist) {
 		double t[2];
 		if (!comm.template collect<2>(seq_prev, t)) {
@@ -415,6 +453,8 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 				comm_abort(st);
 			return;
 		}
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			NB_TL(k, 7);
 		gq_n = t[1];
 		if (blockIdx.x == 0 && threadIdx.x == 0) {
 			st->gg[(k + 1) % 3u] = t[0];   // the gate of K1(k+1)
@@ -450,6 +490,8 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 			p[i] = __dadd_rn(-qv[b], __dmul_rn(beta, pv[b]));
 		}
 	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		NB_TL(k, 8);
 }
 
 // FUSED: this iteration's step lengths from the reduced {g.q, q.Aq, g.g} and the previous iteration's
@@ -765,6 +807,11 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 		set_error("this solver mode needs the streamed SpMV path (slice too wide or NBGPU_SPMV_PATH=reg)");
 		return NBGPU_ERR_ARG;
 	}
+	// the init kernel keeps the plan's visit order (halo slices last); K1 hides them in the slack of the
+	// warps that have no slice in the final partial round (sell_stream.cuh: place_halo_slices)
+	SellView VK = R.V;
+	if (Comm::kDist && stream && !getenv("NBGPU_DIST_HALO_LAST"))
+		place_halo_slices(&VK, (uint32_t)scfg.grid * kStreamWarps);
 	const bool seq = R.seq_dots;
 	const bool pdl = R.pdl && !seq;
 	double *partials = seq ? nullptr : R.partials;
@@ -844,16 +891,16 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 				e = by_layout(layout, [&](auto L) {
 					constexpr int kL = decltype(L)::value;
 					return jacobi ? launch_on(pdl, krylov_fspmv_kernel<true, kL, Comm>, scfg.grid, kBlock,
-								  scfg.smem_bytes, k, R.V, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
+								  scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
 								  (const double *)R.g, R.s, partials, st, tl)
 						      : launch_on(pdl, krylov_fspmv_kernel<false, kL, Comm>, scfg.grid, kBlock,
-								  scfg.smem_bytes, k, R.V, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
+								  scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
 								  (const double *)R.g, R.s, partials, st, tl);
 				});
 			else if (stream)
 				e = by_layout(layout, [&](auto L) {
 					return launch_on(pdl, krylov_spmv_stream_kernel<decltype(L)::value, Comm>, scfg.grid, kBlock,
-							 scfg.smem_bytes, k, R.V, scfg, comm, halo_k(k), msg_k1(k), R.v_ext, R.w,
+							 scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext, R.w,
 							 partials, st, tl);
 				});
 			else

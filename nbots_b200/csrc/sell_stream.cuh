@@ -161,6 +161,7 @@ struct SellView {
 	// and `late()` -- the wait for the halo -- is only called before visit index late_from.
 	uint32_t visit_shift = 0;
 	uint32_t late_from = 0xFFFFFFFFu;
+	uint32_t late_to = 0xFFFFFFFFu;   // visits [late_from, late_to) are the halo-reading ones
 	uint32_t uniform_width = 0;   // != 0: slice s starts at s * uniform_width (no offset loads)
 	// rank-local block (HALO kernels): row r is column r + col_shift of the block's column space
 	// "lower halo | owned | upper halo" (even, a multiple of 16)
@@ -287,7 +288,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 		const uint32_t row = A.perm ? row_ahead : s * kSliceRows + lane;
 		if (A.perm && s64 + total_warps < A.n_slices)
 			row_ahead = __ldg(A.perm + (size_t)slice_of(s64 + total_warps) * kSliceRows + lane);
-		if (!late_done && s64 >= A.late_from) {
+		if (!late_done && s64 >= A.late_from && s64 < A.late_to) {
 			late_done = true;
 			if (!late()) {
 				// drain the stages that are in flight for visits n .. n + stages - 1
@@ -513,7 +514,7 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			x_row = gather1(x + crow);   // row without a stored diagonal
 		body(row, acc, diag, x_row, pre_value);
 		};   // slice_work
-		if (HALO && s64 >= A.late_from)
+		if (HALO && s64 >= A.late_from && s64 < A.late_to)
 			slice_work(std::true_type{});
 		else
 			slice_work(std::false_type{});
@@ -522,6 +523,27 @@ __device__ __forceinline__ void sell_stream_rows(const SellView A, const double 
 			parity ^= 1u;
 		}
 	}
+}
+
+// host: WHERE in the visit order the halo-reading slices of a rank-local block go.  The plan puts them last
+// (visit indices [late_from, n)).  With slices dealt round-robin over W warps, the warps without a slice in the
+// final partial round have one slice of slack: a halo slice costs ~3 us more than an interior one (flag wait
+// with a system-scope acquire, gathers served from L2 instead of L1), so the halo slices are moved to the END
+// OF THE LAST FULL ROUND, onto exactly those warps -- late enough for the halo to have arrived (tens of
+// microseconds after the push at the kernel's start), and off the kernel's critical path.
+inline void place_halo_slices(SellView *V, uint32_t total_warps)
+{
+	const uint32_t n = V->n_slices;
+	if (V->late_from >= n || total_warps == 0)
+		return;   // no halo
+	const uint32_t n_h = n - V->late_from, rem = n % total_warps;
+	if (rem == 0 || n < total_warps || n_h > total_warps - rem)
+		return;   // no slack to hide them in: leave them last
+	const uint32_t v_end = (n / total_warps) * total_warps;
+	// last halo slice = visit_shift - 1 (circularly); it gets visit index v_end - 1
+	V->visit_shift = (uint32_t)(((uint64_t)V->visit_shift + n - v_end) % n);
+	V->late_from = v_end - n_h;
+	V->late_to = v_end;
 }
 
 // host: choose ring depth / CTAs per SM for a matrix; returns false when the
