@@ -252,8 +252,19 @@ krylov_init_stream_kernel(SellView A, StreamConfig cfg, Comm comm, unsigned long
 }
 
 // CLASSIC K1: gate, (halo push,) w = A p, pw = p.w
+// Row-partitioned: the CTA carries ONE MORE WARP than the streaming ones (k1_block<Comm>()).  It does nothing but
+// the halo push (PeerComm::push_halo) and leaves.  Slices are dealt statically over the streaming warps, so
+// the 5-6 us a pushing warp spends (index load, value load, peer stores, system fence until NVLink
+// acknowledges, ticket) would come out of the kernel's tail one for one if a streaming warp did it (measured
+// with the phase timeline: K1 24.5 -> 30 us going from one rank to two; scripts/dist_timeline.py).
+template <typename Comm>
+constexpr int k1_block()
+{
+	return Comm::kDist ? kBlock + 32 : kBlock;
+}
+
 template <int LAYOUT, typename Comm>
-__global__ void __launch_bounds__(kBlock, kStreamCtas)
+__global__ void __launch_bounds__(k1_block<Comm>(), kStreamCtas)
 krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigned long long seq_halo,
 			  unsigned long long seq_red, const double *p_ext, double *__restrict__ w, double *partials,
 			  KrylovState *st, int ticketless)
@@ -261,6 +272,15 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[1] = {0.0};
 	bool active = true;
+	if (Comm::kDist && threadIdx.x >= kBlock) {   // the push warp
+		pdl_wait();
+		const int failed = comm.failed();
+		active = iteration_gate(k, st) && !failed;
+		pdl_launch_dependents();
+		if (active)
+			comm.push_halo(p_ext + A.col_shift, 0, seq_halo, &st->push_ticket);
+		return;
+	}
 	sell_stream_rows<(LAYOUT & 1) != 0, false, (LAYOUT & 2) != 0, Comm::kDist>(
 		A, p_ext, cfg, smem,
 		[&] {
@@ -269,8 +289,6 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 			active = iteration_gate(k, st) && !failed;
 			if (blockIdx.x == 0 && threadIdx.x == 0)
 				NB_TL(k, 0);
-			if (active)
-				comm.push_halo(p_ext + A.col_shift, 0, seq_halo, &st->push_ticket);
 			return active;
 		},
 		[&] {
@@ -517,7 +535,7 @@ __device__ __forceinline__ void fused_store(uint32_t k, const double (&tot)[3], 
 // FUSED K1: gate, (halo push,) s = A v with v = q (Jacobi) or g (plain CG); g.v, v.s, g.g reduced
 // together; the CTA that finishes the reduction (and the exchange) derives this iteration's a and b.
 template <bool JACOBI, int LAYOUT, typename Comm>
-__global__ void __launch_bounds__(kBlock, kStreamCtas)
+__global__ void __launch_bounds__(k1_block<Comm>(), kStreamCtas)
 krylov_fspmv_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigned long long seq_halo,
 		    unsigned long long seq_red, const double *v_ext, const double *g, double *__restrict__ s,
 		    double *partials, KrylovState *st, int ticketless)
@@ -526,13 +544,20 @@ krylov_fspmv_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigne
 	double dots[3] = {0.0, 0.0, 0.0};   // g.v, v.s, g.g
 	bool active = true;
 	const uint32_t N = A.N;
+	if (Comm::kDist && threadIdx.x >= kBlock) {   // the push warp (see krylov_spmv_stream_kernel)
+		pdl_wait();
+		const int failed = comm.failed();
+		active = iteration_gate(k, st) && !failed;
+		pdl_launch_dependents();
+		if (active)
+			comm.push_halo(v_ext + A.col_shift, 0, seq_halo, &st->push_ticket);
+		return;
+	}
 	sell_stream_rows<(LAYOUT & 1) != 0, false, (LAYOUT & 2) != 0, Comm::kDist>(
 		A, v_ext, cfg, smem,
 		[&] {
 			const int failed = comm.failed();   // loaded beside the gate's state line, not behind it
 			active = iteration_gate(k, st) && !failed;
-			if (active)
-				comm.push_halo(v_ext + A.col_shift, 0, seq_halo, &st->push_ticket);
 			return active;
 		},
 		[&] { return comm.wait_halo(0, seq_halo); },
@@ -802,7 +827,7 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 		return jacobi ? (const void *)krylov_fspmv_kernel<true, kL, Comm>
 			      : (const void *)krylov_fspmv_kernel<false, kL, Comm>;
 	});
-	const bool stream = stream_config(A, sk, &scfg) && stream_config(A, ik, &icfg);
+	const bool stream = stream_config(A, sk, &scfg, k1_block<Comm>()) && stream_config(A, ik, &icfg);
 	if (!stream && (fused || Comm::kDist)) {
 		set_error("this solver mode needs the streamed SpMV path (slice too wide or NBGPU_SPMV_PATH=reg)");
 		return NBGPU_ERR_ARG;
@@ -890,16 +915,16 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 			if (stream && fused)
 				e = by_layout(layout, [&](auto L) {
 					constexpr int kL = decltype(L)::value;
-					return jacobi ? launch_on(pdl, krylov_fspmv_kernel<true, kL, Comm>, scfg.grid, kBlock,
+					return jacobi ? launch_on(pdl, krylov_fspmv_kernel<true, kL, Comm>, scfg.grid, k1_block<Comm>(),
 								  scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
 								  (const double *)R.g, R.s, partials, st, tl)
-						      : launch_on(pdl, krylov_fspmv_kernel<false, kL, Comm>, scfg.grid, kBlock,
+						      : launch_on(pdl, krylov_fspmv_kernel<false, kL, Comm>, scfg.grid, k1_block<Comm>(),
 								  scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
 								  (const double *)R.g, R.s, partials, st, tl);
 				});
 			else if (stream)
 				e = by_layout(layout, [&](auto L) {
-					return launch_on(pdl, krylov_spmv_stream_kernel<decltype(L)::value, Comm>, scfg.grid, kBlock,
+					return launch_on(pdl, krylov_spmv_stream_kernel<decltype(L)::value, Comm>, scfg.grid, k1_block<Comm>(),
 							 scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext, R.w,
 							 partials, st, tl);
 				});

@@ -548,6 +548,6 @@ inline void place_halo_slices(SellView *V, uint32_t total_warps)
 
 // host: choose ring depth / CTAs per SM for a matrix; returns false when the
 // widest slice does not fit (the register-path kernels are used instead)
-bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cfg);
+bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cfg, int block = kBlock);
 
 }  // namespace nbgpu

@@ -44,7 +44,7 @@ spmv_stream_kernel(SellView A, StreamConfig cfg, const double *__restrict__ x, d
 // per CTA = 8 warps x stages x stage_bytes; two CTAs per SM (16 consumer warps)
 // are preferred, one is accepted for wide slices.  Env overrides for tuning:
 // NBGPU_STREAM_STAGES, NBGPU_STREAM_CTAS; NBGPU_SPMV_PATH=reg disables the path.
-bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cfg)
+bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cfg, int block)
 {
 	const char *path = getenv("NBGPU_SPMV_PATH");
 	if (path && path[0] == 'r')
@@ -77,7 +77,7 @@ bool stream_config(const nbgpu_matrix_s *A, const void *kernel, StreamConfig *cf
 			continue;
 		}
 		int per_sm = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, cfg->smem_bytes) !=
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, cfg->smem_bytes) !=
 			    cudaSuccess ||
 		    per_sm < 1) {
 			cudaGetLastError();
