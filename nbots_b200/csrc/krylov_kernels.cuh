@@ -252,19 +252,24 @@ krylov_init_stream_kernel(SellView A, StreamConfig cfg, Comm comm, unsigned long
 }
 
 // CLASSIC K1: gate, (halo push,) w = A p, pw = p.w
-// Row-partitioned: the CTA carries ONE MORE WARP than the streaming ones (k1_block<Comm>()).  It does nothing but
-// the halo push (PeerComm::push_halo) and leaves.  Slices are dealt statically over the streaming warps, so
-// the 5-6 us a pushing warp spends (index load, value load, peer stores, system fence until NVLink
-// acknowledges, ticket) would come out of the kernel's tail one for one if a streaming warp did it (measured
-// with the phase timeline: K1 24.5 -> 30 us going from one rank to two; scripts/dist_timeline.py).
-template <typename Comm>
+// Row-partitioned, PUSH_WARP: the CTA carries ONE MORE WARP than the streaming ones.  It does nothing but the
+// halo push (PeerComm::push_halo) and leaves.  Slices are dealt statically over the streaming warps, so the
+// 5-6 us a pushing warp spends (index load, value load, peer stores, system fence until NVLink acknowledges,
+// ticket) come out of the kernel's tail one for one when a streaming warp does it (measured with the phase
+// timeline: K1 24.5 -> 30 us going from one rank to two; scripts/dist_timeline.py).  The price: 22 warps per
+// SM leave 80 registers per thread instead of 96, which costs a bandwidth-bound K1 8 % (8 M dof per rank:
+// 212 -> 229 us).  The host therefore uses the extra warp only where the fixed 5 us are the larger loss
+// (krylov_run: rows per rank below kPushWarpMaxRows); without it the last streaming warp of the first CTAs
+// pushes.
+constexpr uint32_t kPushWarpMaxRows = 3000000;
+template <bool PUSH_WARP>
 constexpr int k1_block()
 {
-	return Comm::kDist ? kBlock + 32 : kBlock;
+	return PUSH_WARP ? kBlock + 32 : kBlock;
 }
 
-template <int LAYOUT, typename Comm>
-__global__ void __launch_bounds__(k1_block<Comm>(), kStreamCtas)
+template <int LAYOUT, typename Comm, bool PUSH_WARP = false>
+__global__ void __launch_bounds__(k1_block<PUSH_WARP>(), kStreamCtas)
 krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigned long long seq_halo,
 			  unsigned long long seq_red, const double *p_ext, double *__restrict__ w, double *partials,
 			  KrylovState *st, int ticketless)
@@ -272,7 +277,7 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 	extern __shared__ __align__(128) unsigned char smem[];
 	double dots[1] = {0.0};
 	bool active = true;
-	if (Comm::kDist && threadIdx.x >= kBlock) {   // the push warp
+	if (PUSH_WARP && threadIdx.x >= kBlock) {
 		pdl_wait();
 		const int failed = comm.failed();
 		active = iteration_gate(k, st) && !failed;
@@ -289,6 +294,8 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 			active = iteration_gate(k, st) && !failed;
 			if (blockIdx.x == 0 && threadIdx.x == 0)
 				NB_TL(k, 0);
+			if (!PUSH_WARP && active)
+				comm.push_halo(p_ext + A.col_shift, 0, seq_halo, &st->push_ticket);
 			return active;
 		},
 		[&] {
@@ -534,8 +541,8 @@ __device__ __forceinline__ void fused_store(uint32_t k, const double (&tot)[3], 
 
 // FUSED K1: gate, (halo push,) s = A v with v = q (Jacobi) or g (plain CG); g.v, v.s, g.g reduced
 // together; the CTA that finishes the reduction (and the exchange) derives this iteration's a and b.
-template <bool JACOBI, int LAYOUT, typename Comm>
-__global__ void __launch_bounds__(k1_block<Comm>(), kStreamCtas)
+template <bool JACOBI, int LAYOUT, typename Comm, bool PUSH_WARP = false>
+__global__ void __launch_bounds__(k1_block<PUSH_WARP>(), kStreamCtas)
 krylov_fspmv_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigned long long seq_halo,
 		    unsigned long long seq_red, const double *v_ext, const double *g, double *__restrict__ s,
 		    double *partials, KrylovState *st, int ticketless)
@@ -544,7 +551,7 @@ krylov_fspmv_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigne
 	double dots[3] = {0.0, 0.0, 0.0};   // g.v, v.s, g.g
 	bool active = true;
 	const uint32_t N = A.N;
-	if (Comm::kDist && threadIdx.x >= kBlock) {   // the push warp (see krylov_spmv_stream_kernel)
+	if (PUSH_WARP && threadIdx.x >= kBlock) {   // see krylov_spmv_stream_kernel
 		pdl_wait();
 		const int failed = comm.failed();
 		active = iteration_gate(k, st) && !failed;
@@ -558,6 +565,8 @@ krylov_fspmv_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigne
 		[&] {
 			const int failed = comm.failed();   // loaded beside the gate's state line, not behind it
 			active = iteration_gate(k, st) && !failed;
+			if (!PUSH_WARP && active)
+				comm.push_halo(v_ext + A.col_shift, 0, seq_halo, &st->push_ticket);
 			return active;
 		},
 		[&] { return comm.wait_halo(0, seq_halo); },
@@ -798,6 +807,17 @@ struct KrylovRun {
 
 // The host loop: init, chunks of iterations, polling one chunk behind.  Returns NBGPU_OK /
 // NBGPU_NOT_CONVERGED / an error; *k_final = iterations performed (also when the exchange failed).
+// compile-time switch for K1's extra push warp; single-GPU code never instantiates it
+template <typename Comm, typename F>
+auto by_push_warp(bool push_warp, F f)
+{
+	if constexpr (Comm::kDist) {
+		if (push_warp)
+			return f(std::true_type{});
+	}
+	return f(std::false_type{});
+}
+
 template <typename Comm>
 int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reached)
 {
@@ -820,14 +840,21 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 		return jacobi ? (const void *)krylov_init_stream_kernel<true, kL, Comm>
 			      : (const void *)krylov_init_stream_kernel<false, kL, Comm>;
 	});
+	// the extra halo-push warp of K1 (see krylov_spmv_stream_kernel): NBGPU_DIST_PUSH_WARP=0|1 overrides
+	const bool push_warp = Comm::kDist && (getenv("NBGPU_DIST_PUSH_WARP") ? atoi(getenv("NBGPU_DIST_PUSH_WARP")) != 0
+										   : A->N <= kPushWarpMaxRows);
+	const int k1_threads = push_warp ? k1_block<true>() : k1_block<false>();
 	const void *sk = by_layout(layout, [&](auto L) {
 		constexpr int kL = decltype(L)::value;
-		if (!fused)
-			return (const void *)krylov_spmv_stream_kernel<kL, Comm>;
-		return jacobi ? (const void *)krylov_fspmv_kernel<true, kL, Comm>
-			      : (const void *)krylov_fspmv_kernel<false, kL, Comm>;
+		return by_push_warp<Comm>(push_warp, [&](auto PW) {
+			constexpr bool kPW = decltype(PW)::value;
+			if (!fused)
+				return (const void *)krylov_spmv_stream_kernel<kL, Comm, kPW>;
+			return jacobi ? (const void *)krylov_fspmv_kernel<true, kL, Comm, kPW>
+				      : (const void *)krylov_fspmv_kernel<false, kL, Comm, kPW>;
+		});
 	});
-	const bool stream = stream_config(A, sk, &scfg, k1_block<Comm>()) && stream_config(A, ik, &icfg);
+	const bool stream = stream_config(A, sk, &scfg, k1_threads) && stream_config(A, ik, &icfg);
 	if (!stream && (fused || Comm::kDist)) {
 		set_error("this solver mode needs the streamed SpMV path (slice too wide or NBGPU_SPMV_PATH=reg)");
 		return NBGPU_ERR_ARG;
@@ -915,18 +942,24 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 			if (stream && fused)
 				e = by_layout(layout, [&](auto L) {
 					constexpr int kL = decltype(L)::value;
-					return jacobi ? launch_on(pdl, krylov_fspmv_kernel<true, kL, Comm>, scfg.grid, k1_block<Comm>(),
-								  scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
-								  (const double *)R.g, R.s, partials, st, tl)
-						      : launch_on(pdl, krylov_fspmv_kernel<false, kL, Comm>, scfg.grid, k1_block<Comm>(),
-								  scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext,
-								  (const double *)R.g, R.s, partials, st, tl);
+					return by_push_warp<Comm>(push_warp, [&](auto PW) {
+						constexpr bool kPW = decltype(PW)::value;
+						return jacobi ? launch_on(pdl, krylov_fspmv_kernel<true, kL, Comm, kPW>, scfg.grid,
+									  k1_threads, scfg.smem_bytes, k, VK, scfg, comm, halo_k(k),
+									  msg_k1(k), R.v_ext, (const double *)R.g, R.s, partials, st, tl)
+							      : launch_on(pdl, krylov_fspmv_kernel<false, kL, Comm, kPW>, scfg.grid,
+									  k1_threads, scfg.smem_bytes, k, VK, scfg, comm, halo_k(k),
+									  msg_k1(k), R.v_ext, (const double *)R.g, R.s, partials, st, tl);
+					});
 				});
 			else if (stream)
 				e = by_layout(layout, [&](auto L) {
-					return launch_on(pdl, krylov_spmv_stream_kernel<decltype(L)::value, Comm>, scfg.grid, k1_block<Comm>(),
-							 scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k), R.v_ext, R.w,
-							 partials, st, tl);
+					constexpr int kL = decltype(L)::value;
+					return by_push_warp<Comm>(push_warp, [&](auto PW) {
+						return launch_on(pdl, krylov_spmv_stream_kernel<kL, Comm, decltype(PW)::value>, scfg.grid,
+								 k1_threads, scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k),
+								 R.v_ext, R.w, partials, st, tl);
+					});
 				});
 			else
 				e = launch_on(pdl, krylov_spmv_kernel, sgrid, kBlock, 0, k, N, A->n_slices, A->d_slice_off, A->d_perm,
