@@ -221,4 +221,15 @@ int nbgpu_cg_host(const nbgpu_matrix_t *A, const double *b, double *x, uint32_t 
 	return solve_host(A, b, x, max_iter, tolerance, niter_performed, tolerance_reached, false);
 }
 
+#ifdef NB_TIMELINE
+/* diagnostic builds only: the %globaltimer stamps of the last single-GPU solve, [512][10] */
+int nbgpu_krylov_timeline(unsigned long long *out)
+{
+	NB_INIT();
+	NB_CUDA(cudaStreamSynchronize(ctx().stream));
+	NB_CUDA(cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * kTlIters * kTlSlots));
+	return NBGPU_OK;
+}
+#endif
+
 }  // extern "C"

@@ -313,12 +313,12 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 		});
 	if (!active || !partials)
 		return;
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		NB_TL(k, 9);
 	if (!Comm::kDist && ticketless) {
 		cta_store_partials<1>(dots, partials);   // K2's CTAs sum them (common.cuh)
 		return;
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0)
-		NB_TL(k, 9);
 	double tot[1];
 	if (grid_reduce<1>(dots, partials, &st->ticket, tot)) {
 		if (threadIdx.x == 0)
@@ -384,6 +384,8 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 		// ticketless: K1's CTAs left their partials, every CTA sums them (same order everywhere)
 		double t[1];
 		cta_sum_partials<1>(partials, n_prev, t);
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			NB_TL(k, 4);
 		pw_k = t[0];
 		if (blockIdx.x == 0 && threadIdx.x == 0)
 			st->pw = pw_k;
@@ -488,6 +490,8 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 	} else if (n_prev) {
 		double t[2];
 		cta_sum_partials<2>(partials + kMaxPartialBlocks, n_prev, t);
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			NB_TL(k, 7);
 		gq_n = t[1];
 		if (blockIdx.x == 0 && threadIdx.x == 0) {
 			st->gg[(k + 1) % 3u] = t[0];
