@@ -37,7 +37,7 @@ struct Context {
 	size_t stage_bytes = 0;
 	double *ws = nullptr;                 // Krylov work vectors (grow-only)
 	size_t ws_bytes = 0;
-	double *partials = nullptr;           // [4][kMaxPartialBlocks] reduction partials
+	double *partials = nullptr;           // [2][kPartialRegion] reduction partials of the two producer kernels
 	void *dev_state = nullptr;            // solver scalars (krylov.cu)
 	void *host_state = nullptr;           // pinned mirror
 	cudaEvent_t poll_ev[2] = {nullptr, nullptr};   // convergence polling (krylov.cu)
@@ -205,9 +205,21 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials,
 // the producer saves -- fence, ticket atomic, the last CTA re-reading and summing the partials, one
 // more store -- sits on the critical path between two dependent kernels; what the consumer adds is a
 // few coalesced L2 loads where it used to read one scalar (one round trip either way).
+// Every consumer CTA reads ALL partials at the same moment: the few cache lines that hold them sit in a few L2
+// slices, and several hundred CTAs queue there (measured on one GPU: 782 CTAs of K3 summing K2's 2 x 444
+// partials 2.2 us, against 1.0 us for one L2 round trip).  The producer therefore stores kPartialReplicas
+// copies (one lane each, fire and forget) and consumer CTA b reads copy b % kPartialReplicas.
+#ifndef NB_PARTIAL_REPLICAS
+#define NB_PARTIAL_REPLICAS 4
+#endif
+constexpr int kPartialReplicas = NB_PARTIAL_REPLICAS;
+constexpr size_t kPartialReplicaStride = 3 * (size_t)kMaxPartialBlocks;              // doubles: [3][kMaxPartialBlocks]
+constexpr size_t kPartialRegion = kPartialReplicas * kPartialReplicaStride;         // one producer kernel's copies
+
 template <int NV>
-__device__ __forceinline__ void cta_store_partials(double (&v)[NV], double *partials)
+__device__ __forceinline__ void cta_store_partials(double (&v)[NV], double *region)
 {
+	static_assert(NV <= 3 && NV * kPartialReplicas <= 32, "one lane per value and copy");
 	__shared__ double sm[NV][kBlock / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -218,22 +230,26 @@ __device__ __forceinline__ void cta_store_partials(double (&v)[NV], double *part
 	}
 	__syncthreads();
 	if (warp == 0) {
+		double mine = 0.0;   // lane l stores value l % NV into copy l / NV
 #pragma unroll
 		for (int k = 0; k < NV; k++) {
 			double s = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
-			s = warp_sum(s);
-			if (lane == 0)
-				partials[k * gridDim.x + blockIdx.x] = s;
+			s = __shfl_sync(0xffffffffu, warp_sum(s), 0);
+			if (lane % NV == k)
+				mine = s;
 		}
+		if (lane < NV * kPartialReplicas)
+			region[(lane / NV) * kPartialReplicaStride + (lane % NV) * gridDim.x + blockIdx.x] = mine;
 	}
 }
 
-// partials: [NV][n_ctas] as written by a grid of n_ctas CTAs; same summation tree as grid_reduce's last CTA
+// region: as written by a grid of n_ctas CTAs; same summation tree as grid_reduce's last CTA
 template <int NV>
-__device__ __forceinline__ void cta_sum_partials(const double *partials, uint32_t n_ctas, double (&out)[NV])
+__device__ __forceinline__ void cta_sum_partials(const double *region, uint32_t n_ctas, double (&out)[NV])
 {
 	__shared__ double sm[NV][kBlock / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const double *partials = region + (blockIdx.x % kPartialReplicas) * kPartialReplicaStride;
 #pragma unroll
 	for (int k = 0; k < NV; k++) {
 		double s = 0.0;

@@ -101,7 +101,7 @@ static int init_device(int device)
 		}
 		cudaGetLastError();
 	}
-	NB_CUDA(nbgpu::dmalloc(&c.partials, sizeof(double) * 4 * kMaxPartialBlocks));
+	NB_CUDA(nbgpu::dmalloc(&c.partials, sizeof(double) * 2 * kPartialRegion));
 	c.ready = true;
 	return NBGPU_OK;
 }

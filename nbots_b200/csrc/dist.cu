@@ -474,6 +474,13 @@ int dist_solve(nbgpu_dist_t *D, nbgpu_dist_plan_t *P, const nbgpu_matrix_t *A, c
 	const uint32_t N = A->N;
 	const size_t Np = ((size_t)N + 1) & ~(size_t)1;
 	const bool fused = krylov_want_fused(A, false);
+	{
+		// Who posts a reduction: the consumer kernel (CLASSIC: 46.6 against 48.4 us per iteration on two GPUs)
+		// or the producer's last CTA (FUSED: 46.1 against 47.8).  NBGPU_DIST_REDUCE=ticket|consumer overrides;
+		// every rank must make the same choice.
+		const char *rd = getenv("NBGPU_DIST_REDUCE");
+		comm.cpost = rd ? (rd[0] == 'c' ? 1 : 0) : (fused ? 0 : 1);
+	}
 	// vectors: the one the SpMV gathers lives in the window (it has halo parts), the rest in the workspace
 	const int n_ws = fused ? (jacobi ? 6 : 4) : (jacobi ? 5 : 3);
 	NB_TRY(ensure_workspace((size_t)n_ws * Np * sizeof(double)));

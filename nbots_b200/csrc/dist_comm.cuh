@@ -225,6 +225,36 @@ __device__ __noinline__ bool collect_slots(DistControl *mine, int world, unsigne
 	return true;
 }
 
+// The same for a rank that already holds its own total in v (consumer-posted reductions): waits for the OTHER
+// ranks' messages only, adds everything in rank order.
+template <int NV>
+__device__ __noinline__ bool collect_others(DistControl *mine, int world, int rank, unsigned long long timeout_ns,
+					    unsigned long long seq, double (&v)[NV])
+{
+	__shared__ double s_val[NV][kMaxRanks];
+	int ok = 1;
+	if ((int)threadIdx.x < world * NV) {
+		const int r = threadIdx.x / NV, c = threadIdx.x % NV;
+		double got = v[0];
+#pragma unroll
+		for (int i = 1; i < NV; i++)
+			got = (c == i) ? v[i] : got;
+		if (r != rank)
+			ok = wait_msg(&mine->msg[seq & 1][r][c], seq, &got, mine, timeout_ns) ? 1 : 0;
+		s_val[c][r] = got;
+	}
+	if (!__syncthreads_and(ok))
+		return false;
+#pragma unroll
+	for (int c = 0; c < NV; c++) {
+		double t = 0.0;
+		for (int r = 0; r < world; r++)
+			t += s_val[c][r];
+		v[c] = t;
+	}
+	return true;
+}
+
 // ---- the two exchange policies of the solver kernels --------------------------------
 // A reduction over the ranks has a PRODUCER side (the CTA that finished the kernel's grid
 // reduction) and a CONSUMER side (the next kernel):
@@ -249,6 +279,9 @@ struct NoComm {
 	__device__ __forceinline__ void post(const double (&)[NV], unsigned long long) const {}
 	template <int NV>
 	__device__ __forceinline__ bool collect(unsigned long long, double (&)[NV]) const { return true; }
+	__host__ __device__ __forceinline__ bool consumer_posts() const { return false; }
+	template <int NV>
+	__device__ __forceinline__ bool exchange(unsigned long long, double (&)[NV]) const { return true; }
 	__device__ __forceinline__ void ack_input(unsigned long long) const {}
 };
 
@@ -264,6 +297,7 @@ struct PeerComm {
 	DistControl *ctrl[kMaxRanks];   // peers' control blocks (own included)
 	int world, rank;
 	uint32_t total_sends;
+	int cpost;                      // reductions are posted by the consumer kernel (see exchange())
 	unsigned long long timeout_ns;
 
 	__device__ __forceinline__ int failed() const { return mine->error; }   // plain: a stale 0 only delays the exit
@@ -323,6 +357,29 @@ struct PeerComm {
 	{
 		post<NV>(v, seq);
 		return collect<NV>(seq, v);
+	}
+	// Consumer-posted reduction: the producer kernel's CTAs only stored their partials (as on one GPU), every
+	// CTA of the consumer has just added them up (v = this rank's total, identical on every CTA).  CTA 0 sends
+	// it to the peers, every CTA waits for the peers' totals and adds all in rank order.  Against the
+	// ticketed producer this takes the ticket pass (fence, atomic round trip, last CTA re-reading the
+	// partials) and the end-of-kernel drain of the NVLink stores off the critical path; the NVLink flight is
+	// exposed in exchange.
+	__host__ __device__ __forceinline__ bool consumer_posts() const { return cpost != 0; }
+	template <int NV>
+	__device__ __forceinline__ bool exchange(unsigned long long seq, double (&v)[NV]) const
+	{
+		if (world == 1)
+			return true;
+		if (blockIdx.x == 0 && (int)threadIdx.x < world * NV) {
+			const int r = threadIdx.x / NV, c = threadIdx.x % NV;
+			double mine_c = v[0];
+#pragma unroll
+			for (int i = 1; i < NV; i++)
+				mine_c = (c == i) ? v[i] : mine_c;
+			if (r != rank)
+				st_msg(&ctrl[r]->msg[seq & 1][rank][c], mine_c, seq);
+		}
+		return collect_others<NV>(mine, world, rank, timeout_ns, seq, v);
 	}
 	// the input halo has been consumed: let the sources push again (SpMV flow control)
 	__device__ __forceinline__ void ack_input(unsigned long long seq) const

@@ -315,7 +315,7 @@ krylov_spmv_stream_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, u
 		return;
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		NB_TL(k, 9);
-	if (!Comm::kDist && ticketless) {
+	if (ticketless) {
 		cta_store_partials<1>(dots, partials);   // K2's CTAs sum them (common.cuh)
 		return;
 	}
@@ -367,10 +367,12 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		NB_TL(k, 3);
-	if (Comm::kDist) {
-		// every CTA collects the ranks' partials of K1 itself (dist_comm.cuh)
+	if (n_prev) {
+		// ticketless: K1's CTAs left their partials, every CTA sums them (same order everywhere); row-partitioned:
+		// CTA 0 posts this rank's total to the peers and every CTA adds the peers' totals (PeerComm::exchange)
 		double t[1];
-		if (!comm.template collect<1>(seq_prev, t)) {
+		cta_sum_partials<1>(partials, n_prev, t);
+		if (Comm::kDist && !comm.template exchange<1>(seq_prev, t)) {
 			if (blockIdx.x == 0)
 				comm_abort(st);
 			return;
@@ -380,10 +382,14 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 		pw_k = t[0];
 		if (blockIdx.x == 0 && threadIdx.x == 0)
 			st->pw = pw_k;   // K3 reads it
-	} else if (n_prev) {
-		// ticketless: K1's CTAs left their partials, every CTA sums them (same order everywhere)
+	} else if (Comm::kDist) {
+		// ticketed producer: every CTA collects the ranks' partials of K1 itself (dist_comm.cuh)
 		double t[1];
-		cta_sum_partials<1>(partials, n_prev, t);
+		if (!comm.template collect<1>(seq_prev, t)) {
+			if (blockIdx.x == 0)
+				comm_abort(st);
+			return;
+		}
 		if (blockIdx.x == 0 && threadIdx.x == 0)
 			NB_TL(k, 4);
 		pw_k = t[0];
@@ -419,10 +425,10 @@ krylov_update_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_p
 	}
 	if (!partials)
 		return;   // reference-order reductions are done by seq_dot_kernel
-	if (!Comm::kDist && ticketless) {
+	if (ticketless) {
 		if (!JACOBI)
 			dots[1] = dots[0];
-		cta_store_partials<2>(dots, partials + kMaxPartialBlocks);   // K3's CTAs sum them
+		cta_store_partials<2>(dots, partials + kPartialRegion);   // K3's CTAs sum them
 		return;
 	}
 	double tot[2];
@@ -473,9 +479,10 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		NB_TL(k, 6);
-	if (Comm::kDist) {
+	if (n_prev) {
 		double t[2];
-		if (!comm.template collect<2>(seq_prev, t)) {
+		cta_sum_partials<2>(partials + kPartialRegion, n_prev, t);
+		if (Comm::kDist && !comm.template exchange<2>(seq_prev, t)) {
 			if (blockIdx.x == 0)
 				comm_abort(st);
 			return;
@@ -487,9 +494,13 @@ krylov_dir_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_prev
 			st->gg[(k + 1) % 3u] = t[0];   // the gate of K1(k+1)
 			st->gq[(k + 1) & 1] = t[1];
 		}
-	} else if (n_prev) {
+	} else if (Comm::kDist) {
 		double t[2];
-		cta_sum_partials<2>(partials + kMaxPartialBlocks, n_prev, t);
+		if (!comm.template collect<2>(seq_prev, t)) {
+			if (blockIdx.x == 0)
+				comm_abort(st);
+			return;
+		}
 		if (blockIdx.x == 0 && threadIdx.x == 0)
 			NB_TL(k, 7);
 		gq_n = t[1];
@@ -587,7 +598,7 @@ krylov_fspmv_kernel(uint32_t k, SellView A, StreamConfig cfg, Comm comm, unsigne
 		});
 	if (!active)
 		return;
-	if (!Comm::kDist && ticketless) {
+	if (ticketless) {
 		if (!JACOBI)
 			dots[2] = dots[0];
 		cta_store_partials<3>(dots, partials);   // K2's CTAs sum them and derive a, b
@@ -639,10 +650,10 @@ krylov_fupdate_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_
 	double alpha = st->alpha[k & 1], beta = st->beta;
 	if (done)
 		return;
-	if (Comm::kDist) {
-		// every CTA collects the ranks' partials of K1 and derives a, b
+	if (n_prev) {
 		double t[3];
-		if (!comm.template collect<3>(seq_prev, t)) {
+		cta_sum_partials<3>(partials, n_prev, t);
+		if (Comm::kDist && !comm.template exchange<3>(seq_prev, t)) {
 			if (blockIdx.x == 0)
 				comm_abort(st);
 			return;
@@ -650,9 +661,14 @@ krylov_fupdate_kernel(uint32_t k, uint32_t N, Comm comm, unsigned long long seq_
 		fused_scalars(k, t, st, &alpha, &beta);
 		if (blockIdx.x == 0 && threadIdx.x == 0)
 			fused_store(k, t, alpha, beta, st);   // slots other than the ones this kernel's CTAs read
-	} else if (n_prev) {
+	} else if (Comm::kDist) {
+		// ticketed producer: every CTA collects the ranks' partials of K1 and derives a, b
 		double t[3];
-		cta_sum_partials<3>(partials, n_prev, t);
+		if (!comm.template collect<3>(seq_prev, t)) {
+			if (blockIdx.x == 0)
+				comm_abort(st);
+			return;
+		}
 		fused_scalars(k, t, st, &alpha, &beta);
 		if (blockIdx.x == 0 && threadIdx.x == 0)
 			fused_store(k, t, alpha, beta, st);
@@ -811,11 +827,12 @@ struct KrylovRun {
 
 // The host loop: init, chunks of iterations, polling one chunk behind.  Returns NBGPU_OK /
 // NBGPU_NOT_CONVERGED / an error; *k_final = iterations performed (also when the exchange failed).
-// compile-time switch for K1's extra push warp; single-GPU code never instantiates it
-template <typename Comm, typename F>
+// compile-time switch for K1's extra push warp.  Only the row-partitioned kernels of the blocked layouts (the
+// 2-dof FEM matrices) have the variant: at 80 registers the per-entry layouts would spill.
+template <typename Comm, int LAYOUT, typename F>
 auto by_push_warp(bool push_warp, F f)
 {
-	if constexpr (Comm::kDist) {
+	if constexpr (Comm::kDist && (LAYOUT & 1) != 0) {
 		if (push_warp)
 			return f(std::true_type{});
 	}
@@ -846,11 +863,12 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 	});
 	// the extra halo-push warp of K1 (see krylov_spmv_stream_kernel): NBGPU_DIST_PUSH_WARP=0|1 overrides
 	const bool push_warp = Comm::kDist && (getenv("NBGPU_DIST_PUSH_WARP") ? atoi(getenv("NBGPU_DIST_PUSH_WARP")) != 0
-										   : A->N <= kPushWarpMaxRows);
+										   : A->N <= kPushWarpMaxRows) &&
+			       (layout & 1) != 0;
 	const int k1_threads = push_warp ? k1_block<true>() : k1_block<false>();
 	const void *sk = by_layout(layout, [&](auto L) {
 		constexpr int kL = decltype(L)::value;
-		return by_push_warp<Comm>(push_warp, [&](auto PW) {
+		return by_push_warp<Comm, kL>(push_warp, [&](auto PW) {
 			constexpr bool kPW = decltype(PW)::value;
 			if (!fused)
 				return (const void *)krylov_spmv_stream_kernel<kL, Comm, kPW>;
@@ -890,7 +908,7 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 	}
 
 	// ticketless reductions (single GPU, parallel-tree dots, streamed K1): see common.cuh
-	const bool tless = !Comm::kDist && !seq && stream && !getenv("NBGPU_TICKETED");
+	const bool tless = (!Comm::kDist || comm.consumer_posts()) && !seq && stream && !getenv("NBGPU_TICKETED");
 	const int tl = tless ? 1 : 0;
 	const uint32_t n_k1 = tless ? (uint32_t)scfg.grid : 0u, n_k2 = tless ? (uint32_t)ugrid : 0u;
 	// message / halo sequence numbers: one reduction message for the init kernel, then 2 (CLASSIC) or
@@ -946,7 +964,7 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 			if (stream && fused)
 				e = by_layout(layout, [&](auto L) {
 					constexpr int kL = decltype(L)::value;
-					return by_push_warp<Comm>(push_warp, [&](auto PW) {
+					return by_push_warp<Comm, kL>(push_warp, [&](auto PW) {
 						constexpr bool kPW = decltype(PW)::value;
 						return jacobi ? launch_on(pdl, krylov_fspmv_kernel<true, kL, Comm, kPW>, scfg.grid,
 									  k1_threads, scfg.smem_bytes, k, VK, scfg, comm, halo_k(k),
@@ -959,7 +977,7 @@ int krylov_run(KrylovRun &R, const Comm &comm, uint32_t *niter, double *tol_reac
 			else if (stream)
 				e = by_layout(layout, [&](auto L) {
 					constexpr int kL = decltype(L)::value;
-					return by_push_warp<Comm>(push_warp, [&](auto PW) {
+					return by_push_warp<Comm, kL>(push_warp, [&](auto PW) {
 						return launch_on(pdl, krylov_spmv_stream_kernel<kL, Comm, decltype(PW)::value>, scfg.grid,
 								 k1_threads, scfg.smem_bytes, k, VK, scfg, comm, halo_k(k), msg_k1(k),
 								 R.v_ext, R.w, partials, st, tl);

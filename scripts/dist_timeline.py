@@ -29,6 +29,8 @@ nxt = tl.reshape(512, 10).astype(np.int64)[51:451]
 med = lambda a: float(np.median(a))
 out = {"rank": rank, "us_per_iter": round(ms * 1e3 / 500, 2),
        "K1 start -> CTA0 rows done": med(t[:, 9] - t[:, 0]),
+       "K1 CTA0 rows done -> K2 CTA0 past wait": med(t[:, 3] - t[:, 9]),
+       "K2 CTA0 past wait -> K3 CTA0 past wait": med(t[:, 6] - t[:, 3]),
        "K1 start -> last CTA reduced (posts)": med(t[:, 1] - t[:, 0]),
        "K1 start -> halo arrived (CTA0 late wait)": med(t[:, 2] - t[:, 0]) if t[:, 2].any() else None,
        "K1 posted -> K2 CTA0 past wait": med(t[:, 3] - t[:, 1]),
