@@ -466,6 +466,14 @@ int nbgpu_dist_plan_info(const nbgpu_dist_plan_t *plan, uint32_t *N_loc,
 /* n_lo halo columns lie below the owned range; layout as nbgpu_dist_ext_layout */
 int nbgpu_dist_plan_layout(const nbgpu_dist_plan_t *plan, uint32_t *n_lo,
 			   uint32_t *off_own, uint32_t *off_up, uint32_t *ext_len);
+/* The order in which the SpMV kernels visit this rank's 32-row slices: visit index v
+ * -> slice (v + visit_shift) mod n_slices; the slices that read halo columns are the
+ * visits [late_from, late_to).  total_warps = 0: the plan's own order (they come last;
+ * init kernel, nbgpu_dist_spmv); total_warps = streaming warps of the solver's SpMV
+ * kernel: they end with the last full round of slices when the final partial round
+ * leaves enough warps without a slice (hides their wait for the neighbours). */
+int nbgpu_dist_plan_visit_order(const nbgpu_dist_plan_t *plan, uint32_t total_warps,
+				uint32_t *visit_shift, uint32_t *late_from, uint32_t *late_to);
 /* the halo columns (global row ids, ascending => grouped by owner) */
 int nbgpu_dist_plan_halo_ids(const nbgpu_dist_plan_t *plan, uint32_t *halo_global);
 int nbgpu_dist_plan_local_cols(const nbgpu_dist_plan_t *plan, uint32_t *cols_local);

@@ -129,6 +129,7 @@ SIGNATURES = {
     "nbgpu_matrix_create_local": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, f64p, vpp]),
     "nbgpu_dist_ext_layout": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, u32p]),
     "nbgpu_dist_plan_layout": (C.c_int, [C.c_void_p, u32p, u32p, u32p, u32p]),
+    "nbgpu_dist_plan_visit_order": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u32p, u32p]),
     "nbgpu_dist_connect_local": (C.c_int, [C.c_void_p, vpp, C.POINTER(C.c_int)]),
     "nbgpu_set_pcg_mode": (C.c_int, [C.c_int]),
     "nbgpu_thread_bind_device": (C.c_int, [C.c_int]),

@@ -226,6 +226,22 @@ int nbgpu_dist_plan_layout(const nbgpu_dist_plan_t *P, uint32_t *n_lo, uint32_t 
 	return NBGPU_OK;
 }
 
+int nbgpu_dist_plan_visit_order(const nbgpu_dist_plan_t *P, uint32_t total_warps, uint32_t *visit_shift,
+				uint32_t *late_from, uint32_t *late_to)
+{
+	NB_ARG(P != nullptr && visit_shift != nullptr && late_from != nullptr && late_to != nullptr);
+	SellView V;
+	V.n_slices = (P->N_loc + kSliceRows - 1) / kSliceRows;
+	V.visit_shift = P->visit_shift;
+	V.late_from = P->late_from;
+	if (total_warps)
+		place_halo_slices(&V, total_warps);
+	*visit_shift = V.visit_shift;
+	*late_from = V.late_from;
+	*late_to = std::min(V.late_to, V.n_slices);
+	return NBGPU_OK;
+}
+
 int nbgpu_dist_plan_halo_ids(const nbgpu_dist_plan_t *P, uint32_t *halo_global)
 {
 	NB_ARG(P != nullptr && (halo_global != nullptr || P->n_halo == 0));

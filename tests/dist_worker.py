@@ -60,6 +60,30 @@ def run_cpu(rank, world):
                     np.where(glob < r1, dc.off_own + glob - r0,
                              dc.off_up + np.searchsorted(dc.halo_global, glob) - dc.n_lo))
     assert np.array_equal(dc.cols_local, want.astype(np.uint32))
+    # visit order of the 32-row slices (nbgpu_dist_plan_visit_order): every slice that reads a halo column is a
+    # "late" visit, with the plan's own order (late ones last) and with the solver kernel's (late ones at the end
+    # of the last full round, on warps that have no slice in the final partial round)
+    import ctypes as C
+    from nbots_b200 import capi
+    n_sl = (dc.N_loc + 31) // 32
+    row_of = np.repeat(np.arange(dc.N_loc), rs[r0:r1])
+    halo_entry = (dc.cols_local < dc.off_own) | (dc.cols_local >= dc.off_up)
+    halo_slices = set(np.unique(row_of[halo_entry] // 32).tolist())
+    assert (world == 1) == (not halo_slices)
+    for W in (0, 7, 20, 33, n_sl, 2960):
+        sh, lf, lt = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        capi.check(capi.lib().nbgpu_dist_plan_visit_order(dc.plan, W, C.byref(sh), C.byref(lf), C.byref(lt)))
+        sh, lf, lt = sh.value, lf.value, lt.value
+        late = {(v + sh) % n_sl for v in range(min(lf, n_sl), lt)}
+        assert halo_slices <= late, (W, sorted(halo_slices - late))
+        if not halo_slices:
+            assert not late
+            continue
+        assert sh < n_sl and lf < lt <= n_sl
+        if W == 0 or n_sl % W == 0 or n_sl < W or lt - lf > W - n_sl % W:
+            assert lt == n_sl                              # no slack to hide them in: they stay last
+        else:
+            assert lt == (n_sl // W) * W and lf % W >= n_sl % W and lt - lf <= W - n_sl % W
 
     def exchange(v_loc):
         """halo of a distributed vector: what nbots_b200/csrc/dist.cu does with peer stores, here over gloo"""
