@@ -264,6 +264,18 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh,
 				const double *elem_scale, double *d_F,
 				uint32_t *first_bad);
 
+/* The lumped mass vector pipeline_assemble_system fills when its M argument is
+ * not NULL (solid_mechanics/pipeline.c:56-57 zeroed, :216-222 Me[2i] +=
+ * Ni Nj density detJ thickness w over j and the Gauss points, :256-259
+ * M[2v+a] += Me[2i+a] in element order).  d_M: 2 N_nod doubles on the device.
+ * density_void: density of disabled elements (the reference uses 1e-6,
+ * pipeline.c:93-94).  enabled / first_bad / return value as above. */
+int nbgpu_assemble_lumped_mass(const nbgpu_mesh_t *mesh,
+			       const nbgpu_elem_tables_t *tables,
+			       double density, double density_void,
+			       double thickness, const uint8_t *enabled,
+			       double *d_M, uint32_t *first_bad);
+
 /* F[dof[k]] += add[k], k in order (the Neumann part of nb_fem_set_bconditions,
  * solid_mechanics/set_bconditions.c:63-188, flattened by the caller) */
 int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof,

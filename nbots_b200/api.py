@@ -262,6 +262,15 @@ class Mesh:
         check(st, ok=(capi.OK, capi.DISTORTED_ELEMENT))
         return st, bad.value
 
+    def lumped_mass(self, d_M: DeviceBuffer, density, thickness=1.0, enabled=None):
+        """The M vector of pipeline_assemble_system (pipeline.c:216-222, :256-259); returns (status, first bad element)."""
+        en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
+        bad = C.c_uint32(0)
+        st = lib().nbgpu_assemble_lumped_mass(self.h, C.byref(self.tables), density, 1e-6, thickness, _ptr(en, u8p),
+                                              d_M.ptr, C.byref(bad))
+        check(st, ok=(capi.OK, capi.DISTORTED_ELEMENT))
+        return st, bad.value
+
     def compute_strain(self, d_disp: DeviceBuffer, d_strain: DeviceBuffer):
         check(lib().nbgpu_compute_strain(self.h, C.byref(self.tables), d_disp.ptr, d_strain.ptr))
 

@@ -340,6 +340,67 @@ assemble_node_kernel(uint32_t n_rows, uint32_t col_shift, uint32_t nb_max, const
 	F[row0 + 1] = f1;
 }
 
+// ---- lumped mass vector: one thread per node ---------------------------------
+// What pipeline_assemble_system fills when M != NULL (pipeline.c:56-57, :216-222, :256-259): for every element
+// of the node in ascending id, Me[2i] accumulates Ni*Nj*density*detJ*thickness*wp over j inside the Gauss loop
+// (that expression order), and M[2v+a] += Me[2i+a].  Same gather schedule as the stiffness rows, so bit-exact.
+template <int NPE, int NGP>
+__global__ void __launch_bounds__(kBlock)
+lumped_mass_kernel(uint32_t N_nod, const double *__restrict__ nod, const uint32_t *__restrict__ adj,
+		   const uint32_t *__restrict__ n2e_ptr, const uint32_t *__restrict__ n2e,
+		   const uint8_t *__restrict__ enabled, double density, double density_void, double thickness,
+		   double *__restrict__ M, unsigned int *first_bad)
+{
+	const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+	if (node >= N_nod)
+		return;
+	double m = 0.0;
+	for (uint32_t t = n2e_ptr[node]; t < n2e_ptr[node + 1]; t++) {
+		const uint32_t e = n2e[t];
+		uint32_t v[NPE];
+		double xs[NPE], ys[NPE];
+		int li = 0;
+#pragma unroll
+		for (int i = 0; i < NPE; i++) {
+			v[i] = adj[(size_t)e * NPE + i];
+			xs[i] = nod[2 * (size_t)v[i]];
+			ys[i] = nod[2 * (size_t)v[i] + 1];
+		}
+#pragma unroll
+		for (int i = NPE - 1; i >= 0; i--)
+			if (v[i] == node)
+				li = i;   // first local index of this node
+		const double rho = (!enabled || enabled[e]) ? density : density_void;   // pipeline.c:93-98
+		double me = 0.0;
+		bool bad = false;
+#pragma unroll
+		for (int gp = 0; gp < NGP; gp++) {
+			double dx[NPE], dy[NPE];
+			const double detJ = jacobian_gradients<NPE, NGP>(xs, ys, gp, dx, dy);
+			if (detJ < 0)
+				bad = true;   // utils.c:44-47
+			const double wp = c_tab.w[gp];
+			double Ni = c_tab.Ni[gp];
+#pragma unroll
+			for (int i = 1; i < NPE; i++)
+				if (li == i)
+					Ni = c_tab.Ni[i * NGP + gp];
+#pragma unroll
+			for (int j = 0; j < NPE; j++) {
+				const double Nj = c_tab.Ni[j * NGP + gp];
+				me += Ni * Nj * rho * detJ * thickness * wp;   // pipeline.c:216-221
+			}
+		}
+		if (bad) {
+			atomicMin(first_bad, e);
+			continue;
+		}
+		m += me;
+	}
+	M[2 * (size_t)node] = m;
+	M[2 * (size_t)node + 1] = m;
+}
+
 // ---- ATOMIC / COLOR: one thread per element --------------------------------
 template <int NPE, int NGP, bool ATOMIC>
 __global__ void __launch_bounds__(128)
@@ -1111,6 +1172,48 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
 	if (first_bad)
 		*first_bad = h_flags[0];
 	return h_flags[0] != 0xFFFFFFFFu ? NBGPU_DISTORTED_ELEMENT : NBGPU_OK;
+}
+
+int nbgpu_assemble_lumped_mass(const nbgpu_mesh_t *mesh_c, const nbgpu_elem_tables_t *tables, double density,
+			       double density_void, double thickness, const uint8_t *enabled, double *d_M,
+			       uint32_t *first_bad)
+{
+	NB_INIT();
+	nbgpu_mesh_t *m = const_cast<nbgpu_mesh_t *>(mesh_c);
+	NB_ARG(m != nullptr && d_M != nullptr);
+	Context &c = ctx();
+	NB_TRY(upload_tables(tables, m->npe));
+	const uint8_t *d_en = nullptr;
+	if (enabled) {
+		NB_CUDA(cudaMemcpyAsync(m->d_enabled, enabled, m->N_elems, cudaMemcpyHostToDevice, c.stream));
+		d_en = m->d_enabled;
+	}
+	unsigned int *d_flag = nullptr;
+	NB_CUDA(nbgpu::dmalloc(&d_flag, sizeof(unsigned int)));
+	const unsigned int init_flag = 0xFFFFFFFFu;
+	NB_CUDA(cudaMemcpyAsync(d_flag, &init_flag, sizeof(init_flag), cudaMemcpyHostToDevice, c.stream));
+	const int grid = (int)((m->N_nod + kBlock - 1) / kBlock);
+	if (m->npe == 3)
+		lumped_mass_kernel<3, 1><<<std::max(grid, 1), kBlock, 0, c.stream>>>(
+			m->N_nod, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, density, density_void, thickness, d_M,
+			d_flag);
+	else
+		lumped_mass_kernel<4, 4><<<std::max(grid, 1), kBlock, 0, c.stream>>>(
+			m->N_nod, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, density, density_void, thickness, d_M,
+			d_flag);
+	NB_LAUNCHED();
+	unsigned int h_flag = 0xFFFFFFFFu;
+	cudaError_t e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(h_flag), cudaMemcpyDeviceToHost, c.stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(c.stream);
+	nbgpu::dfree(d_flag);
+	if (e != cudaSuccess) {
+		set_error("lumped mass: %s", cudaGetErrorString(e));
+		return NBGPU_ERR_CUDA;
+	}
+	if (first_bad)
+		*first_bad = h_flag;
+	return h_flag != 0xFFFFFFFFu ? NBGPU_DISTORTED_ELEMENT : NBGPU_OK;
 }
 
 int nbgpu_vector_add_entries(double *d_F, uint32_t n, const uint32_t *dof, const double *add)

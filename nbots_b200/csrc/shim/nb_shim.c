@@ -482,11 +482,6 @@ int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh
 	ENTER();
 	resolve();
 	LEAVE();
-	if (M != NULL) {
-		/* the lumped mass vector belongs to the dynamic drivers, outside this hot path */
-		fprintf(stderr, "nbots_b200: pipeline_assemble_system with a mass vector is not accelerated\n");
-		return NBGPU_ERR_ARG;
-	}
 	nbgpu_elem_tables_t tab;
 	read_tables(elem, &tab);
 	flat_mesh_t fm;
@@ -524,6 +519,15 @@ int pipeline_assemble_system(nb_sparse_t *K, double *M, double *F, const nb_mesh
 			st = nbgpu_matrix_get_values_rows(dK, K->rows_values);
 			if (st == NBGPU_OK)
 				st = nbgpu_copy_d2h(F, d_F, (size_t)K->N * sizeof(double));
+		}
+		if (st == NBGPU_OK && M != NULL) {
+			/* the lumped mass vector (pipeline.c:56-57, :216-222, :256-259); d_F is free again */
+			st = nbgpu_assemble_lumped_mass(dmesh, &tab, ap.density, ap.density_void, ap.thickness,
+							(const uint8_t *)elements_enabled, d_F, NULL);
+			if (st == NBGPU_DISTORTED_ELEMENT)
+				st = NBGPU_OK;   /* already in `status` */
+			if (st == NBGPU_OK)
+				st = nbgpu_copy_d2h(M, d_F, (size_t)K->N * sizeof(double));
 		}
 	}
 	nbgpu_free(d_F);

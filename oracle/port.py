@@ -55,6 +55,8 @@ def lib():
         L.nbo_assemble.restype = C.c_int
         L.nbo_assemble.argtypes = [C.c_uint32, f64p, C.c_uint32, C.c_int, u32p, C.c_double, C.c_double, C.c_double,
                                    C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p, u64p, u32p, f64p, f64p]
+        L.nbo_lumped_mass.restype = C.c_int
+        L.nbo_lumped_mass.argtypes = [C.c_uint32, f64p, C.c_uint32, C.c_int, u32p, C.c_double, C.c_double, u8p, f64p]
         L.nbo_assemble_scaled.restype = C.c_int
         L.nbo_assemble_scaled.argtypes = [C.c_uint32, f64p, C.c_uint32, C.c_int, u32p, C.c_double, C.c_double,
                                           C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p, f64p,
@@ -182,6 +184,15 @@ def assemble(K: Csr, m, E, nu, density=0.0, self_weight=False, gravity=(0.0, 0.0
                             int(self_weight), gravity[0], gravity[1], analysis, thickness, _p(en, u8p),
                             _p(K.row_ptr, u64p), _p(K.cols, u32p), _p(K.vals, f64p), _p(F, f64p))
     return st, F
+
+
+def lumped_mass(m, density, thickness=1.0, enabled=None):
+    """M of pipeline_assemble_system(K, M != NULL, ...) (pipeline.c:216-222, :256-259)."""
+    M = np.zeros(2 * m.n_nod)
+    en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
+    st = lib().nbo_lumped_mass(m.n_nod, _p(m.nod, f64p), m.n_elems, m.kind, _p(m.adj, u32p), density, thickness,
+                               _p(en, u8p), _p(M, f64p))
+    return st, M
 
 
 def make_bcs(records):

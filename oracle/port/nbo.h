@@ -81,6 +81,12 @@ int nbo_assemble(uint32_t N_nod, const double *nod, uint32_t N_elems,
 		 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
 		 double *F);
 
+/* the lumped mass vector pipeline_assemble_system fills when M != NULL
+ * (pipeline.c:56-57, :216-222, :256-259); 0, or 1 at the first distorted element */
+int nbo_lumped_mass(uint32_t N_nod, const double *nod, uint32_t N_elems,
+		    int elem_type, const uint32_t *adj, double density,
+		    double thickness, const uint8_t *enabled, double *M);
+
 /* nbo_assemble with the product's per-element stiffness factor (not a reference
  * feature; checker for the SIMP-style hook only) */
 int nbo_assemble_scaled(uint32_t N_nod, const double *nod, uint32_t N_elems,

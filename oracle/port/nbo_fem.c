@@ -236,6 +236,52 @@ static int assemble_impl(uint32_t N_nod, const double *nod, uint32_t N_elems,
 	return 0;
 }
 
+/* Lumped mass vector of pipeline_assemble_system(K, M != NULL, ...).
+ * Reference: solid_mechanics/pipeline.c:56-57 (M zeroed), :93-98 (density of a
+ * disabled element 1e-6), :216-222 (Me[2i] += Ni*Nj*density*detJ*thickness*wp
+ * for every j, inside the Gauss loop; both components get the same value),
+ * :256-259 (M[2 v_i + a] += Me[2 i + a], elements in ascending id), :139-161
+ * (stop at the first element with detJ < 0: status 1, M holds the elements
+ * before it). */
+int nbo_lumped_mass(uint32_t N_nod, const double *nod, uint32_t N_elems,
+		    int elem_type, const uint32_t *adj, double density,
+		    double thickness, const uint8_t *enabled, double *M)
+{
+	elem_t el;
+	nbo_elem_tables(elem_type, &el.n, &el.ngp, el.w, el.Ni, el.dpsi,
+			el.deta);
+	uint32_t n = el.n;
+	memset(M, 0, 2 * (size_t)N_nod * sizeof(double));
+	for (uint32_t e = 0; e < N_elems; e++) {
+		const uint32_t *v = adj + (size_t)n * e;
+		double rho = (!enabled || enabled[e]) ? density : 1e-6;
+		double Me[8], dx[4], dy[4];
+		memset(Me, 0, sizeof(Me));
+		for (uint32_t gp = 0; gp < el.ngp; gp++) {
+			double detJ = jacobian_and_gradients(&el, nod, v, gp,
+							     dx, dy);
+			if (detJ < 0)
+				return 1;
+			double wp = el.w[gp];
+			for (uint32_t i = 0; i < n; i++) {
+				double Ni = el.Ni[i * el.ngp + gp];
+				for (uint32_t j = 0; j < n; j++) {
+					double Nj = el.Ni[j * el.ngp + gp];
+					double integral = Ni * Nj * rho * detJ *
+						thickness * wp;
+					Me[2 * i] += integral;
+					Me[2 * i + 1] += integral;
+				}
+			}
+		}
+		for (uint32_t i = 0; i < n; i++) {
+			M[2 * v[i]] += Me[2 * i];
+			M[2 * v[i] + 1] += Me[2 * i + 1];
+		}
+	}
+	return 0;
+}
+
 /* Kirsch solution (infinite plate, hole radius 0.5, far-field sxx = 1e4),
  * same expression as oracle/ref_harness.c so both checkers evaluate the
  * function-valued conditions identically. */

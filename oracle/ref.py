@@ -66,6 +66,9 @@ def lib():
         L.refh_assemble.restype = C.c_int
         L.refh_assemble.argtypes = [C.c_void_p, f64p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
                                     C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p]
+        L.refh_assemble_mass.restype = C.c_int
+        L.refh_assemble_mass.argtypes = [C.c_void_p, f64p, f64p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                         C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p]
         L.refh_bcond_create.restype = C.c_void_p
         L.refh_bcond_destroy.argtypes = [C.c_void_p]
         L.refh_bcond_push.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
@@ -275,6 +278,17 @@ def assemble(K: RefSparse, mesh: RefMesh, elem_type, E, nu, density=0.0, self_we
     st = lib().refh_assemble(K.h, _p(F, f64p), mesh.h, elem_type, E, nu, density, int(self_weight),
                              gravity[0], gravity[1], analysis, thickness, _p(en, u8p))
     return st, F
+
+
+def assemble_with_mass(K: RefSparse, mesh: RefMesh, elem_type, E, nu, density=0.0, self_weight=False,
+                       gravity=(0.0, 0.0), analysis=0, thickness=1.0, enabled=None):
+    """pipeline_assemble_system with M != NULL: returns (status, F, M)."""
+    F = np.zeros(K.N)
+    M = np.zeros(K.N)
+    en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
+    st = lib().refh_assemble_mass(K.h, _p(M, f64p), _p(F, f64p), mesh.h, elem_type, E, nu, density, int(self_weight),
+                                  gravity[0], gravity[1], analysis, thickness, _p(en, u8p))
+    return st, F, M
 
 
 def set_bconditions(mesh: RefMesh, K: RefSparse, F, bc: RefBcond, factor=1.0):

@@ -414,10 +414,34 @@ void refh_constitutive(double E, double nu, int analysis, double D[4])
 	nb_material_destroy(mat);
 }
 
+static int assemble_with(void *K, double *M, double *F, const void *hp,
+			 int elem_type, double E, double nu, double density,
+			 int self_weight, double gx, double gy, int analysis,
+			 double thickness, const uint8_t *enabled);
+
 int refh_assemble(void *K, double *F, const void *hp, int elem_type,
 		  double E, double nu, double density, int self_weight,
 		  double gx, double gy, int analysis, double thickness,
 		  const uint8_t *enabled /* NULL = all */)
+{
+	return assemble_with(K, NULL, F, hp, elem_type, E, nu, density,
+			     self_weight, gx, gy, analysis, thickness, enabled);
+}
+
+/* the same call with the lumped mass vector wanted (M: 2 N_nod doubles) */
+int refh_assemble_mass(void *K, double *M, double *F, const void *hp,
+		       int elem_type, double E, double nu, double density,
+		       int self_weight, double gx, double gy, int analysis,
+		       double thickness, const uint8_t *enabled)
+{
+	return assemble_with(K, M, F, hp, elem_type, E, nu, density,
+			     self_weight, gx, gy, analysis, thickness, enabled);
+}
+
+static int assemble_with(void *K, double *M, double *F, const void *hp,
+			 int elem_type, double E, double nu, double density,
+			 int self_weight, double gx, double gy, int analysis,
+			 double thickness, const uint8_t *enabled)
 {
 	const refh_mesh_t *h = hp;
 	nb_fem_elem_t *e = nb_fem_elem_create(elem_type ? NB_QUAD_LINEAR
@@ -434,7 +458,7 @@ int refh_assemble(void *K, double *F, const void *hp, int elem_type,
 		for (uint32_t i = 0; i < N_el; i++)
 			en[i] = enabled[i] != 0;
 	}
-	int status = pipeline_assemble_system(K, NULL, F, h->mesh, e, mat,
+	int status = pipeline_assemble_system(K, M, F, h->mesh, e, mat,
 					      self_weight != 0, gravity,
 					      (nb_analysis2D_t)analysis,
 					      &params, en);

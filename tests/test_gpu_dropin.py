@@ -44,6 +44,13 @@ SCRIPT = textwrap.dedent('''
         K = ref.RefSparse.from_mesh(rm)
         st, F = ref.assemble(K, rm, kind, float(g["E"]), float(g["nu"]), **kw)
         assert st == 0 and np.array_equal(K.export()[2], g["K_pre"]) and np.array_equal(F, g["F_pre"]), name
+        # (1b) the same entry with the lumped mass vector wanted (M != NULL, pipeline.c:56-57, :216-222, :256-259)
+        gm = golden("lumped_mass")
+        K2 = ref.RefSparse.from_mesh(rm)
+        st, F2, M2 = ref.assemble_with_mass(K2, rm, kind, float(g["E"]), float(g["nu"]), density=float(gm["density"]),
+                                            self_weight=True, gravity=(0.3, -9.81), analysis=int(g["analysis"]),
+                                            thickness=float(gm["thickness"]), enabled=gm[name + "/mask"])
+        assert st == 0 and np.array_equal(M2, gm[name + "/masked/M"]), name
         # (2) the reference's own BC code (host C, not shimmed), then its solver entry -> shim
         bc = ref.RefBcond()
         for r in bc_records(g):

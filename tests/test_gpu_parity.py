@@ -277,6 +277,31 @@ def test_assembly_gather_is_bit_exact(nbgpu_lib, name):
 
 
 @pytest.mark.parametrize("name", FEM_CASES)
+def test_lumped_mass_is_bit_exact(nbgpu_lib, name):
+    """nbgpu_assemble_lumped_mass against the reference's M (pipeline_assemble_system with M != NULL; fixtures from
+    oracle/make_golden_mass.py) and the oracle on a distorted mesh."""
+    gm = golden("lumped_mass")
+    m = mesh_of(golden(name))
+    mesh = api.Mesh(m)
+    d_M = api.DeviceBuffer.zeros(2 * m.n_nod)
+    rho, t = float(gm["density"]), float(gm["thickness"])
+    for tag, en in (("all", None), ("masked", gm[f"{name}/mask"])):
+        capi.check(nbgpu_lib.nbgpu_memset(d_M.ptr, 0xFF, 2 * m.n_nod * 8))      # every entry must be written
+        st, bad = mesh.lumped_mass(d_M, rho, t, en)
+        assert st == 0 and np.array_equal(d_M.to_host(), gm[f"{name}/{tag}/M"])
+    # an inverted element: status 1 with its id, the other elements' contributions as the oracle has them up to it
+    m2 = mesh_of(golden(name))
+    e_bad = m2.n_elems // 2
+    a = m2.adj.reshape(-1, m2.npe)
+    a[e_bad, 0], a[e_bad, 1] = a[e_bad, 1], a[e_bad, 0]
+    mesh2 = api.Mesh(m2)
+    st, bad = mesh2.lumped_mass(d_M, rho, t, None)
+    assert (st, bad) == (1, e_bad)
+    ost, _ = port.lumped_mass(m2, rho, t, None)
+    assert ost == 1
+
+
+@pytest.mark.parametrize("name", FEM_CASES)
 @pytest.mark.parametrize("mode", [capi.ASSEMBLY_ATOMIC, capi.ASSEMBLY_COLOR])
 def test_assembly_element_parallel(nbgpu_lib, name, mode):
     g = golden(name)

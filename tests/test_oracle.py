@@ -42,6 +42,28 @@ def test_port_reproduces_reference_fem_pipeline(name):
     assert np.array_equal(port.constitutive(float(g["E"]), float(g["nu"]), int(g["analysis"])), g["D"])
 
 
+@pytest.mark.parametrize("name", FEM_CASES)
+def test_port_reproduces_reference_lumped_mass(name):
+    """M of pipeline_assemble_system(K, M != NULL, ...) (pipeline.c:216-222, :256-259): the restatement against the
+    vectors oracle/make_golden_mass.py took from the reference, all elements enabled and with a mask."""
+    gm = golden("lumped_mass")
+    m = mesh_of(golden(name))
+    rho, t = float(gm["density"]), float(gm["thickness"])
+    for tag, en in (("all", None), ("masked", gm[f"{name}/mask"])):
+        st, M = port.lumped_mass(m, rho, t, en)
+        assert st == 0 and np.array_equal(M, gm[f"{name}/{tag}/M"])
+    # both components of a node carry the same mass; the total is density * thickness * area when nothing is masked
+    st, M = port.lumped_mass(m, rho, t, None)
+    assert np.array_equal(M[0::2], M[1::2])
+    x, y = m.nod[0::2], m.nod[1::2]
+    a = m.adj.reshape(-1, m.npe)
+    area = 0.0
+    for k in range(m.npe):                                   # shoelace over every element
+        i, j = a[:, k], a[:, (k + 1) % m.npe]
+        area += 0.5 * np.sum(x[i] * y[j] - x[j] * y[i])
+    assert abs(M[0::2].sum() - rho * t * area) <= 1e-11 * rho * t * area
+
+
 def test_reference_known_answers():
     """The two asserts of the reference's own FEM suite (utest/.../static_elasticity2D.c:118,136)."""
     g = golden("beam_cantilever_trg1000")
