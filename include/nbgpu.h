@@ -264,6 +264,20 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh,
 				const double *elem_scale, double *d_F,
 				uint32_t *first_bad);
 
+/* The assembly loop of the reference's damage driver, DMG_pipeline_assemble_system
+ * (solid_mechanics/static_damage2D.c:474-569): as nbgpu_assemble_elasticity2d,
+ * with the constitutive matrix of Gauss point j of element k multiplied by
+ * (1 - gp_damage[k * N_gp + j]) (:530-536; the void material of a disabled element
+ * is scaled too).  gp_damage: host array, N_elems * N_gp doubles.  GATHER schedule on
+ * a 2-dof blocked matrix only (NBGPU_ERR_ARG otherwise); bit-exact.  The reference
+ * leaves its loop silently at a distorted element; here that is status 1. */
+int nbgpu_assemble_elasticity2d_damage(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh,
+				       const nbgpu_elem_tables_t *tables,
+				       const nbgpu_assembly_params_t *params,
+				       const uint8_t *enabled,
+				       const double *gp_damage, double *d_F,
+				       uint32_t *first_bad);
+
 /* The lumped mass vector pipeline_assemble_system fills when its M argument is
  * not NULL (solid_mechanics/pipeline.c:56-57 zeroed, :216-222 Me[2i] +=
  * Ni Nj density detJ thickness w over j and the Gauss points, :256-259

@@ -244,7 +244,8 @@ class Mesh:
         return n.value, colors[:self.m.n_elems]
 
     def assemble(self, K: Matrix, d_F: DeviceBuffer, E, nu, density=0.0, self_weight=False, gravity=(0.0, 0.0),
-                 analysis=0, thickness=1.0, enabled=None, elem_scale=None, mode=capi.ASSEMBLY_GATHER):
+                 analysis=0, thickness=1.0, enabled=None, elem_scale=None, mode=capi.ASSEMBLY_GATHER, gp_damage=None):
+        """pipeline_assemble_system; with gp_damage the damage driver's loop (static_damage2D.c:474-569)."""
         p = capi.AssemblyParams()
         D = constitutive_matrix(E, nu, analysis)
         for k in range(4):
@@ -257,6 +258,12 @@ class Mesh:
         en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
         sc = None if elem_scale is None else _f64(elem_scale)
         bad = C.c_uint32(0)
+        if gp_damage is not None:
+            assert elem_scale is None
+            st = lib().nbgpu_assemble_elasticity2d_damage(K.h, self.h, C.byref(self.tables), C.byref(p), _ptr(en, u8p),
+                                                          _ptr(_f64(gp_damage), f64p), d_F.ptr, C.byref(bad))
+            check(st, ok=(capi.OK, capi.DISTORTED_ELEMENT))
+            return st, bad.value
         st = lib().nbgpu_assemble_elasticity2d(K.h, self.h, C.byref(self.tables), C.byref(p), _ptr(en, u8p),
                                                _ptr(sc, f64p), d_F.ptr, C.byref(bad))
         check(st, ok=(capi.OK, capi.DISTORTED_ELEMENT))

@@ -110,6 +110,8 @@ SIGNATURES = {
     "nbgpu_constitutive_matrix": (C.c_int, [C.c_double, C.c_double, C.c_int, f64p]),
     "nbgpu_assemble_elasticity2d": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ElemTables),
                                               C.POINTER(AssemblyParams), u8p, f64p, C.c_void_p, u32p]),
+    "nbgpu_assemble_elasticity2d_damage": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ElemTables),
+                                                     C.POINTER(AssemblyParams), u8p, f64p, C.c_void_p, u32p]),
     "nbgpu_assemble_lumped_mass": (C.c_int, [C.c_void_p, C.POINTER(ElemTables), C.c_double, C.c_double, C.c_double,
                                              u8p, C.c_void_p, u32p]),
     "nbgpu_vector_add_entries": (C.c_int, [C.c_void_p, C.c_uint32, u32p, f64p]),

@@ -224,12 +224,16 @@ assemble_gather_kernel(uint32_t n_rows, uint32_t col_shift, const double *__rest
 constexpr int kNodeThreads = 128;   // 8 slices per CTA
 constexpr int kNodeMaxBlocks = 24;  // 2x2 blocks per node row held in (dynamic) shared memory: 36 bytes per block and thread
 
-template <int NPE, int NGP>
+// DAMAGE: the damage driver's loop (static_damage2D.c:474-569) -- the constitutive matrix of Gauss point gp of
+// element e is multiplied by (1 - gp_damage[e NGP + gp]) (:530-536), for the void material of a disabled
+// element as well.  A separate instantiation: the plain kernel's code is unchanged.
+template <int NPE, int NGP, bool DAMAGE = false>
 __global__ void __launch_bounds__(kNodeThreads)
 assemble_node_kernel(uint32_t n_rows, uint32_t col_shift, uint32_t nb_max, const double *__restrict__ nod,
 		     const uint32_t *__restrict__ adj, const uint32_t *__restrict__ n2e_ptr,
 		     const uint32_t *__restrict__ n2e, const uint8_t *__restrict__ enabled,
-		     const double *__restrict__ scale, AsmParams P, const uint32_t *__restrict__ slice_off,
+		     const double *__restrict__ scale, const double *__restrict__ gp_damage, AsmParams P,
+		     const uint32_t *__restrict__ slice_off,
 		     const uint32_t *__restrict__ perm, const uint32_t *__restrict__ bcol, double *__restrict__ val,
 		     double *__restrict__ F, unsigned int *first_bad, int *pattern_miss)
 {
@@ -271,8 +275,8 @@ assemble_node_kernel(uint32_t n_rows, uint32_t col_shift, uint32_t nb_max, const
 		for (int i = NPE - 1; i >= 0; i--)
 			if (v[i] == node)
 				li = i;   // first local index of this node
-		double D[4], rho;
-		element_material(P, enabled, scale, e, D, rho);
+		double D0[4], rho;
+		element_material(P, enabled, scale, e, D0, rho);
 		const double fx = P.self_weight ? P.gx * rho : 0.0, fy = P.self_weight ? P.gy * rho : 0.0;
 		double k0[2 * NPE], k1[2 * NPE];   // rows (2 li) and (2 li + 1) of Ke
 #pragma unroll
@@ -287,6 +291,11 @@ assemble_node_kernel(uint32_t n_rows, uint32_t col_shift, uint32_t nb_max, const
 			if (detJ < 0)
 				bad = true;   // utils.c:44-47
 			const double wp = c_tab.w[gp];
+			double D[4];
+			const double undamaged = DAMAGE ? 1.0 - gp_damage[(size_t)e * NGP + gp] : 1.0;
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				D[k] = DAMAGE ? D0[k] * undamaged : D0[k];
 			double dxi = dx[0], dyi = dy[0], Ni = c_tab.Ni[gp];
 #pragma unroll
 			for (int i = 1; i < NPE; i++)
@@ -903,11 +912,30 @@ int build_coloring(nbgpu_mesh_t *m)
 
 template <int NPE, int NGP>
 int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int mode, const uint8_t *d_en,
-		    const double *d_scale, double *d_F, unsigned int *d_bad, int *d_miss)
+		    const double *d_scale, const double *d_damage, double *d_F, unsigned int *d_bad, int *d_miss)
 {
 	Context &c = ctx();
-	if (mode == NBGPU_ASSEMBLY_GATHER && K->blocked && K->max_width <= 2 * kNodeMaxBlocks && (K->N & 1u) == 0 &&
-	    !getenv("NBGPU_ASSEMBLY_ROWS")) {
+	const bool node_form = mode == NBGPU_ASSEMBLY_GATHER && K->blocked && K->max_width <= 2 * kNodeMaxBlocks &&
+			       (K->N & 1u) == 0;
+	if (d_damage) {
+		// the damage driver's loop exists in the node-parallel schedule only
+		if (!node_form) {
+			set_error("per-Gauss-point damage needs the GATHER schedule on a 2-dof blocked matrix");
+			return NBGPU_ERR_ARG;
+		}
+		const uint32_t pairs = K->n_slices * 16u;
+		const uint32_t nb_max = (K->max_width + 1) / 2;
+		const size_t smem = (size_t)nb_max * kNodeThreads * (4 * sizeof(double) + sizeof(uint32_t));
+		if (smem > 48 * 1024)
+			NB_CUDA(cudaFuncSetAttribute(assemble_node_kernel<NPE, NGP, true>,
+						     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		assemble_node_kernel<NPE, NGP, true><<<(pairs + kNodeThreads - 1) / kNodeThreads, kNodeThreads, smem, c.stream>>>(
+			K->N, K->col_shift, nb_max, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, d_damage, P,
+			K->d_slice_off, K->d_perm, K->d_bcol, K->d_val, d_F, d_bad, d_miss);
+		NB_LAUNCHED();
+		return NBGPU_OK;
+	}
+	if (node_form && !getenv("NBGPU_ASSEMBLY_ROWS")) {
 		// node-parallel form: overwrites every entry of the rows, no reset needed
 		const uint32_t pairs = K->n_slices * 16u;
 		const uint32_t nb_max = (K->max_width + 1) / 2;
@@ -916,8 +944,8 @@ int launch_assembly(nbgpu_matrix_t *K, nbgpu_mesh_t *m, const AsmParams &P, int 
 			NB_CUDA(cudaFuncSetAttribute(assemble_node_kernel<NPE, NGP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 						     (int)smem));
 		assemble_node_kernel<NPE, NGP><<<(pairs + kNodeThreads - 1) / kNodeThreads, kNodeThreads, smem, c.stream>>>(
-			K->N, K->col_shift, nb_max, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, P, K->d_slice_off,
-			K->d_perm, K->d_bcol, K->d_val, d_F, d_bad, d_miss);
+			K->N, K->col_shift, nb_max, m->d_nod, m->d_adj, m->d_n2e_ptr, m->d_n2e, d_en, d_scale, nullptr, P,
+			K->d_slice_off, K->d_perm, K->d_bcol, K->d_val, d_F, d_bad, d_miss);
 		NB_LAUNCHED();
 	} else if (mode == NBGPU_ASSEMBLY_GATHER) {
 		NB_CUDA(cudaMemsetAsync(K->d_val, 0, K->stored * sizeof(double), c.stream));   // nb_sparse_reset (pipeline.c:54)
@@ -1108,10 +1136,33 @@ int nbgpu_mesh_coloring(nbgpu_mesh_t *m, uint32_t *n_colors, uint8_t *colors)
 	return NBGPU_OK;
 }
 
+static int assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c, const nbgpu_elem_tables_t *tables,
+				 const nbgpu_assembly_params_t *params, const uint8_t *enabled,
+				 const double *elem_scale, const double *gp_damage, double *d_F, uint32_t *first_bad);
+
 int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
 				const nbgpu_elem_tables_t *tables, const nbgpu_assembly_params_t *params,
 				const uint8_t *enabled, const double *elem_scale, double *d_F,
 				uint32_t *first_bad)
+{
+	return assemble_elasticity2d(K, mesh_c, tables, params, enabled, elem_scale, nullptr, d_F, first_bad);
+}
+
+int nbgpu_assemble_elasticity2d_damage(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
+				       const nbgpu_elem_tables_t *tables, const nbgpu_assembly_params_t *params,
+				       const uint8_t *enabled, const double *gp_damage, double *d_F,
+				       uint32_t *first_bad)
+{
+	if (!gp_damage) {
+		set_error("gp_damage is NULL");
+		return NBGPU_ERR_ARG;
+	}
+	return assemble_elasticity2d(K, mesh_c, tables, params, enabled, nullptr, gp_damage, d_F, first_bad);
+}
+
+static int assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c, const nbgpu_elem_tables_t *tables,
+				 const nbgpu_assembly_params_t *params, const uint8_t *enabled,
+				 const double *elem_scale, const double *gp_damage, double *d_F, uint32_t *first_bad)
 {
 	NB_INIT();
 	nbgpu_mesh_t *m = const_cast<nbgpu_mesh_t *>(mesh_c);
@@ -1142,22 +1193,39 @@ int nbgpu_assemble_elasticity2d(nbgpu_matrix_t *K, const nbgpu_mesh_t *mesh_c,
 					cudaMemcpyHostToDevice, c.stream));
 		d_scale = m->d_scale;
 	}
+	double *d_damage = nullptr;
+	if (gp_damage) {
+		const size_t n_gp = (size_t)m->N_elems * (m->npe == 3 ? 1 : 4);
+		NB_CUDA(nbgpu::dmalloc(&d_damage, n_gp * sizeof(double)));
+		cudaError_t ce = cudaMemcpyAsync(d_damage, gp_damage, n_gp * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+		if (ce != cudaSuccess) {
+			nbgpu::dfree(d_damage);
+			NB_CUDA(ce);
+		}
+	}
 	// flags: [0] lowest distorted element id, [1] pattern miss
 	unsigned int *d_flags = nullptr;
-	NB_CUDA(nbgpu::dmalloc(&d_flags, 2 * sizeof(unsigned int)));
+	{
+		cudaError_t ce = nbgpu::dmalloc(&d_flags, 2 * sizeof(unsigned int));
+		if (ce != cudaSuccess) {
+			nbgpu::dfree(d_damage);
+			NB_CUDA(ce);
+		}
+	}
 	const unsigned int init_flags[2] = {0xFFFFFFFFu, 0u};
 	NB_CUDA(cudaMemcpyAsync(d_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, c.stream));
 	// nb_sparse_reset (pipeline.c:54) and the zeroing of F (pipeline.c:57) are done by the schedules themselves
 	int st;
 	if (m->npe == 3)
-		st = launch_assembly<3, 1>(K, m, P, params->mode, d_en, d_scale, d_F, d_flags, (int *)(d_flags + 1));
+		st = launch_assembly<3, 1>(K, m, P, params->mode, d_en, d_scale, d_damage, d_F, d_flags, (int *)(d_flags + 1));
 	else
-		st = launch_assembly<4, 4>(K, m, P, params->mode, d_en, d_scale, d_F, d_flags, (int *)(d_flags + 1));
+		st = launch_assembly<4, 4>(K, m, P, params->mode, d_en, d_scale, d_damage, d_F, d_flags, (int *)(d_flags + 1));
 	unsigned int h_flags[2] = {0xFFFFFFFFu, 0u};
 	cudaError_t e = cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c.stream);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(c.stream);
 	nbgpu::dfree(d_flags);
+	nbgpu::dfree(d_damage);
 	if (st != NBGPU_OK)
 		return st;
 	if (e != cudaSuccess) {

@@ -55,6 +55,10 @@ def lib():
         L.nbo_assemble.restype = C.c_int
         L.nbo_assemble.argtypes = [C.c_uint32, f64p, C.c_uint32, C.c_int, u32p, C.c_double, C.c_double, C.c_double,
                                    C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p, u64p, u32p, f64p, f64p]
+        L.nbo_assemble_damage.restype = C.c_int
+        L.nbo_assemble_damage.argtypes = [C.c_uint32, f64p, C.c_uint32, C.c_int, u32p, C.c_double, C.c_double,
+                                          C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p, f64p,
+                                          u64p, u32p, f64p, f64p]
         L.nbo_lumped_mass.restype = C.c_int
         L.nbo_lumped_mass.argtypes = [C.c_uint32, f64p, C.c_uint32, C.c_int, u32p, C.c_double, C.c_double, u8p, f64p]
         L.nbo_assemble_scaled.restype = C.c_int
@@ -170,9 +174,16 @@ def constitutive(E, nu, analysis):
 
 
 def assemble(K: Csr, m, E, nu, density=0.0, self_weight=False, gravity=(0.0, 0.0), analysis=0, thickness=1.0,
-             enabled=None, elem_scale=None):
+             enabled=None, elem_scale=None, gp_damage=None):
     F = np.zeros(K.N)
     en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
+    if gp_damage is not None:      # the damage driver's loop (static_damage2D.c:474-569)
+        dm = np.ascontiguousarray(gp_damage, dtype=np.float64)
+        st = lib().nbo_assemble_damage(m.n_nod, _p(m.nod, f64p), m.n_elems, m.kind, _p(m.adj, u32p), E, nu, density,
+                                       int(self_weight), gravity[0], gravity[1], analysis, thickness, _p(en, u8p),
+                                       _p(dm, f64p), _p(K.row_ptr, u64p), _p(K.cols, u32p), _p(K.vals, f64p),
+                                       _p(F, f64p))
+        return st, F
     if elem_scale is not None:
         sc = np.ascontiguousarray(elem_scale, dtype=np.float64)
         st = lib().nbo_assemble_scaled(m.n_nod, _p(m.nod, f64p), m.n_elems, m.kind, _p(m.adj, u32p), E, nu, density,

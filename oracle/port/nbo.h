@@ -81,6 +81,16 @@ int nbo_assemble(uint32_t N_nod, const double *nod, uint32_t N_elems,
 		 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
 		 double *F);
 
+/* the damage driver's assembly loop (static_damage2D.c:474-569): D of Gauss
+ * point j of element k times (1 - gp_damage[k N_gp + j]) */
+int nbo_assemble_damage(uint32_t N_nod, const double *nod, uint32_t N_elems,
+			int elem_type, const uint32_t *adj, double E, double nu,
+			double density, int self_weight, double gx, double gy,
+			int analysis, double thickness, const uint8_t *enabled,
+			const double *gp_damage,
+			const uint64_t *row_ptr, const uint32_t *cols, double *vals,
+			double *F);
+
 /* the lumped mass vector pipeline_assemble_system fills when M != NULL
  * (pipeline.c:56-57, :216-222, :256-259); 0, or 1 at the first distorted element */
 int nbo_lumped_mass(uint32_t N_nod, const double *nod, uint32_t N_elems,

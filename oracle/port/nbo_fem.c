@@ -111,7 +111,7 @@ static int assemble_impl(uint32_t N_nod, const double *nod, uint32_t N_elems,
 			 int elem_type, const uint32_t *adj, double E, double nu,
 			 double density, int self_weight, double gx, double gy,
 			 int analysis, double thickness, const uint8_t *enabled,
-			 const double *elem_scale,
+			 const double *elem_scale, const double *gp_damage,
 			 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
 			 double *F);
 
@@ -124,7 +124,25 @@ int nbo_assemble(uint32_t N_nod, const double *nod, uint32_t N_elems,
 {
 	return assemble_impl(N_nod, nod, N_elems, elem_type, adj, E, nu, density,
 			     self_weight, gx, gy, analysis, thickness, enabled,
-			     NULL, row_ptr, cols, vals, F);
+			     NULL, NULL, row_ptr, cols, vals, F);
+}
+
+/* The damage driver's assembly loop, static_damage2D.c:474-569: as above, with
+ * the constitutive matrix of Gauss point j of element k multiplied by
+ * (1 - gp_damage[k * N_gp + j]) (:530-536) -- applied to the void material of
+ * a disabled element as well.  (The reference leaves its loop silently at a
+ * distorted element, :543-544; here that is status 1.) */
+int nbo_assemble_damage(uint32_t N_nod, const double *nod, uint32_t N_elems,
+			int elem_type, const uint32_t *adj, double E, double nu,
+			double density, int self_weight, double gx, double gy,
+			int analysis, double thickness, const uint8_t *enabled,
+			const double *gp_damage,
+			const uint64_t *row_ptr, const uint32_t *cols, double *vals,
+			double *F)
+{
+	return assemble_impl(N_nod, nod, N_elems, elem_type, adj, E, nu, density,
+			     self_weight, gx, gy, analysis, thickness, enabled,
+			     NULL, gp_damage, row_ptr, cols, vals, F);
 }
 
 /* Extension used only to check the product's SIMP-style hook (the reference has
@@ -140,14 +158,14 @@ int nbo_assemble_scaled(uint32_t N_nod, const double *nod, uint32_t N_elems,
 {
 	return assemble_impl(N_nod, nod, N_elems, elem_type, adj, E, nu, density,
 			     self_weight, gx, gy, analysis, thickness, enabled,
-			     elem_scale, row_ptr, cols, vals, F);
+			     elem_scale, NULL, row_ptr, cols, vals, F);
 }
 
 static int assemble_impl(uint32_t N_nod, const double *nod, uint32_t N_elems,
 			 int elem_type, const uint32_t *adj, double E, double nu,
 			 double density, int self_weight, double gx, double gy,
 			 int analysis, double thickness, const uint8_t *enabled,
-			 const double *elem_scale,
+			 const double *elem_scale, const double *gp_damage,
 			 const uint64_t *row_ptr, const uint32_t *cols, double *vals,
 			 double *F)
 {
@@ -182,23 +200,27 @@ static int assemble_impl(uint32_t N_nod, const double *nod, uint32_t N_elems,
 			if (detJ < 0)
 				return 1;
 			double wp = el.w[gp];
+			double Dr[4] = {D[0], D[1], D[2], D[3]};
+			if (gp_damage)   /* static_damage2D.c:530-536 */
+				for (int k = 0; k < 4; k++)
+					Dr[k] *= (1.0 - gp_damage[(size_t)e * el.ngp + gp]);
 			for (uint32_t i = 0; i < n; i++) {
 				for (uint32_t j = 0; j < n; j++) {
 					Ke[(2 * i) * (2 * n) + 2 * j] +=
-						(dx[i] * dx[j] * D[0] +
-						 dy[i] * dy[j] * D[3]) *
+						(dx[i] * dx[j] * Dr[0] +
+						 dy[i] * dy[j] * Dr[3]) *
 						detJ * thickness * wp;
 					Ke[(2 * i) * (2 * n) + 2 * j + 1] +=
-						(dx[i] * dy[j] * D[1] +
-						 dy[i] * dx[j] * D[3]) *
+						(dx[i] * dy[j] * Dr[1] +
+						 dy[i] * dx[j] * Dr[3]) *
 						detJ * thickness * wp;
 					Ke[(2 * i + 1) * (2 * n) + 2 * j] +=
-						(dy[i] * dx[j] * D[1] +
-						 dx[i] * dy[j] * D[3]) *
+						(dy[i] * dx[j] * Dr[1] +
+						 dx[i] * dy[j] * Dr[3]) *
 						detJ * thickness * wp;
 					Ke[(2 * i + 1) * (2 * n) + 2 * j + 1] +=
-						(dy[i] * dy[j] * D[2] +
-						 dx[i] * dx[j] * D[3]) *
+						(dy[i] * dy[j] * Dr[2] +
+						 dx[i] * dx[j] * Dr[3]) *
 						detJ * thickness * wp;
 				}
 				double integral = el.Ni[i * el.ngp + gp] *

@@ -69,6 +69,9 @@ def lib():
         L.refh_assemble_mass.restype = C.c_int
         L.refh_assemble_mass.argtypes = [C.c_void_p, f64p, f64p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
                                          C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, u8p]
+        L.refh_assemble_damage.restype = None
+        L.refh_assemble_damage.argtypes = [C.c_void_p, f64p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                           C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, f64p, u8p]
         L.refh_bcond_create.restype = C.c_void_p
         L.refh_bcond_destroy.argtypes = [C.c_void_p]
         L.refh_bcond_push.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
@@ -289,6 +292,17 @@ def assemble_with_mass(K: RefSparse, mesh: RefMesh, elem_type, E, nu, density=0.
     st = lib().refh_assemble_mass(K.h, _p(M, f64p), _p(F, f64p), mesh.h, elem_type, E, nu, density, int(self_weight),
                                   gravity[0], gravity[1], analysis, thickness, _p(en, u8p))
     return st, F, M
+
+
+def assemble_damage(K: RefSparse, mesh: RefMesh, elem_type, E, nu, gp_damage, density=0.0, self_weight=False,
+                    gravity=(0.0, 0.0), analysis=0, thickness=1.0, enabled=None):
+    """DMG_pipeline_assemble_system (static_damage2D.c:474-569): D of every Gauss point scaled by 1 - damage."""
+    F = np.zeros(K.N)
+    dm = None if gp_damage is None else np.ascontiguousarray(gp_damage, dtype=np.float64)
+    en = None if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8)
+    lib().refh_assemble_damage(K.h, _p(F, f64p), mesh.h, elem_type, E, nu, density, int(self_weight), gravity[0],
+                               gravity[1], analysis, thickness, _p(dm, f64p), _p(en, u8p))
+    return F
 
 
 def set_bconditions(mesh: RefMesh, K: RefSparse, F, bc: RefBcond, factor=1.0):

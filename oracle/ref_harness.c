@@ -468,6 +468,49 @@ static int assemble_with(void *K, double *M, double *F, const void *hp,
 	return status;
 }
 
+/* static_damage2D.c:474-569, made visible by the Makefile (objcopy); the
+ * prototype is the file's own (static_damage2D.c:52-63) */
+void DMG_pipeline_assemble_system(nb_sparse_t *K, double *M, double *F,
+				  const nb_mesh2D_t *const part,
+				  const nb_fem_elem_t *const elem,
+				  const nb_material_t *const material,
+				  bool enable_self_weight, double gravity[2],
+				  nb_analysis2D_t analysis2D,
+				  nb_analysis2D_params *params2D,
+				  bool enable_computing_damage,
+				  double *damage_elem, bool *elements_enabled);
+
+/* the damage driver's assembly: D of Gauss point j of element k is scaled by
+ * (1 - damage[k * N_gp + j]); damage NULL = no scaling */
+void refh_assemble_damage(void *K, double *F, const void *hp, int elem_type,
+			  double E, double nu, double density, int self_weight,
+			  double gx, double gy, int analysis, double thickness,
+			  const double *damage, const uint8_t *enabled)
+{
+	const refh_mesh_t *h = hp;
+	nb_fem_elem_t *e = nb_fem_elem_create(elem_type ? NB_QUAD_LINEAR
+							: NB_TRG_LINEAR);
+	nb_material_t *mat = make_material(E, nu, density);
+	nb_analysis2D_params params;
+	memset(&params, 0, sizeof(params));
+	params.thickness = thickness;
+	double gravity[2] = {gx, gy};
+	uint32_t N_el = nb_mesh2D_get_N_elems(h->mesh);
+	bool *en = NULL;
+	if (enabled) {
+		en = malloc(N_el * sizeof(bool) + 1);
+		for (uint32_t i = 0; i < N_el; i++)
+			en[i] = enabled[i] != 0;
+	}
+	DMG_pipeline_assemble_system(K, NULL, F, h->mesh, e, mat,
+				     self_weight != 0, gravity,
+				     (nb_analysis2D_t)analysis, &params,
+				     damage != NULL, (double *)damage, en);
+	free(en);
+	nb_material_destroy(mat);
+	nb_fem_elem_destroy(e);
+}
+
 void *refh_bcond_create(void) { return nb_bcond_create(2); }
 void refh_bcond_destroy(void *bc) { nb_bcond_destroy(bc); }
 

@@ -276,6 +276,40 @@ def test_assembly_gather_is_bit_exact(nbgpu_lib, name):
     assert np.array_equal(d_F.to_host(), g["F_pre"])
 
 
+@pytest.mark.parametrize("name", ["beam_cantilever_trg1000", "quad_void_selfweight_24x8"])
+def test_damage_assembly_is_bit_exact(nbgpu_lib, name):
+    """nbgpu_assemble_elasticity2d_damage against K and F of the reference's DMG_pipeline_assemble_system
+    (static_damage2D.c:474-569; fixtures from oracle/make_golden_damage.py), and against the oracle at a larger size."""
+    gd = golden("damage_assembly")
+    g = golden(name)
+    m = mesh_of(g)
+    kw = dict(density=float(gd["density"]), self_weight=True, gravity=tuple(gd["gravity"]),
+              analysis=int(g["analysis"]), thickness=float(gd["thickness"]))
+    mesh = api.Mesh(m)
+    for tag, en in (("all", None), ("masked", gd[f"{name}/mask"])):
+        K = api.Matrix.from_csr(g["rows_size"], g["cols"])
+        d_F = api.DeviceBuffer.zeros(K.N)
+        st, bad = mesh.assemble(K, d_F, float(g["E"]), float(g["nu"]), enabled=en, gp_damage=gd[f"{name}/damage"], **kw)
+        assert st == 0
+        assert np.array_equal(K.values_csr(), gd[f"{name}/{tag}/K"])
+        assert np.array_equal(d_F.to_host(), gd[f"{name}/{tag}/F"])
+    # a larger structured mesh of the same element type, against the oracle
+    m2 = meshgen.structured_mesh(96, 40, 3.0, 1.0, kind=m.kind)
+    rs, cols = port.pattern_from_mesh(m2)
+    rng = np.random.default_rng(9)
+    dmg = rng.random(m2.n_elems * (4 if m2.kind else 1)) * 0.95
+    en2 = (rng.random(m2.n_elems) > 0.1).astype(np.uint8)
+    Kp = port.Csr(rs, cols)
+    st, Fp = port.assemble(Kp, m2, 210e9, 0.3, enabled=en2, gp_damage=dmg, **kw)
+    K2 = api.Matrix.from_csr(rs, cols)
+    d_F2 = api.DeviceBuffer.zeros(K2.N)
+    st2, _ = api.Mesh(m2).assemble(K2, d_F2, 210e9, 0.3, enabled=en2, gp_damage=dmg, **kw)
+    assert st == st2 == 0 and np.array_equal(K2.values_csr(), Kp.vals) and np.array_equal(d_F2.to_host(), Fp)
+    # the element-parallel schedules do not have the loop
+    with pytest.raises(capi.NbgpuError):
+        mesh.assemble(K, d_F, float(g["E"]), float(g["nu"]), gp_damage=gd[f"{name}/damage"], mode=capi.ASSEMBLY_ATOMIC, **kw)
+
+
 @pytest.mark.parametrize("name", FEM_CASES)
 def test_lumped_mass_is_bit_exact(nbgpu_lib, name):
     """nbgpu_assemble_lumped_mass against the reference's M (pipeline_assemble_system with M != NULL; fixtures from

@@ -64,6 +64,27 @@ def test_port_reproduces_reference_lumped_mass(name):
     assert abs(M[0::2].sum() - rho * t * area) <= 1e-11 * rho * t * area
 
 
+@pytest.mark.parametrize("name", ["beam_cantilever_trg1000", "quad_void_selfweight_24x8"])
+def test_port_reproduces_reference_damage_assembly(name):
+    """The damage driver's assembly loop (static_damage2D.c:474-569): the restatement against K and F taken from the
+    reference's own function (oracle/make_golden_damage.py)."""
+    gd = golden("damage_assembly")
+    g = golden(name)
+    m = mesh_of(g)
+    kw = dict(density=float(gd["density"]), self_weight=True, gravity=tuple(gd["gravity"]),
+              analysis=int(g["analysis"]), thickness=float(gd["thickness"]))
+    for tag, en in (("all", None), ("masked", gd[f"{name}/mask"])):
+        K = port.Csr(g["rows_size"], g["cols"])
+        st, F = port.assemble(K, m, float(g["E"]), float(g["nu"]), enabled=en, gp_damage=gd[f"{name}/damage"], **kw)
+        assert st == 0
+        assert np.array_equal(K.vals, gd[f"{name}/{tag}/K"]) and np.array_equal(F, gd[f"{name}/{tag}/F"])
+    # zero damage is pipeline_assemble_system bit for bit (D * 1.0)
+    K0, K1 = port.Csr(g["rows_size"], g["cols"]), port.Csr(g["rows_size"], g["cols"])
+    st, F0 = port.assemble(K0, m, float(g["E"]), float(g["nu"]), gp_damage=np.zeros_like(gd[f"{name}/damage"]), **kw)
+    st, F1 = port.assemble(K1, m, float(g["E"]), float(g["nu"]), **kw)
+    assert np.array_equal(K0.vals, K1.vals) and np.array_equal(F0, F1)
+
+
 def test_reference_known_answers():
     """The two asserts of the reference's own FEM suite (utest/.../static_elasticity2D.c:118,136)."""
     g = golden("beam_cantilever_trg1000")
