@@ -171,6 +171,16 @@ def test_port_matches_live_reference(kind):
     assert np.array_equal(K.export()[2], PK.vals) and np.array_equal(F, F2)
     r1, r2 = K.pcg_jacobi(F, tol=1e-9), PK.pcg_jacobi(F2, tol=1e-9)
     assert r1[0] == r2[0] and r1[2] == r2[2] and np.array_equal(r1[1], r2[1])
+    # the lumped mass vector (M != NULL) and the damage driver's loop on the same perturbed mesh
+    K3 = ref.RefSparse.from_mesh(rm)
+    st, F3, M3 = ref.assemble_with_mass(K3, rm, kind, 5.0, 0.2, **kw)
+    st2, M4 = port.lumped_mass(m, kw["density"], kw["thickness"], en)
+    assert st == st2 == 0 and np.array_equal(M3, M4)
+    dmg = rng.random(m.n_elems * (4 if kind else 1)) * 0.99
+    F5 = ref.assemble_damage(K3, rm, kind, 5.0, 0.2, dmg, **kw)
+    PK3 = port.Csr(prs, pcols)
+    st2, F6 = port.assemble(PK3, m, 5.0, 0.2, gp_damage=dmg, **kw)
+    assert st2 == 0 and np.array_equal(K3.export()[2], PK3.vals) and np.array_equal(F5, F6)
     # a distorted element (clockwise) is reported by both (pipeline.c:158-159)
     m2 = meshgen.structured_mesh(4, 3, 4.0, 3.0, kind=kind)
     npe = m2.npe
