@@ -5,8 +5,9 @@
 // peers map it (CUDA IPC between processes, peer access inside one process) and
 //   * push the boundary entries of the gathered vector straight into the neighbours' halo parts
 //     (plain stores over NVLink), followed by a system-scope release of a sequence number;
-//   * post their partial dot products as self-validating 16-byte messages into one slot per rank
-//     of every peer's control block.
+//   * post their partial dot products (the rank's total, sent by one CTA of the producing or of the
+//     consuming kernel) as self-validating 16-byte messages into one slot per rank of every peer's
+//     control block.
 // Consumers poll THEIR OWN memory.  All ranks add the per-rank partials in rank order, so alpha,
 // beta and the stopping decision are bit-identical on every rank.
 //
@@ -263,9 +264,13 @@ __device__ __noinline__ bool collect_others(DistControl *mine, int world, int ra
 //   collect()  every CTA of the consumer polls the slots in its own memory (one L2 round trip when
 //              the messages are there -- what reading the reduced scalar costs on one GPU) and adds
 //              them in rank order.
+//   exchange() the CONSUMER-posted form (CLASSIC default, see PeerComm::exchange): the producer only stores
+//              per-CTA partials as on one GPU, every consumer CTA adds them up, CTA 0 sends the rank's total
+//              and all CTAs add the peers' totals -- no ticket pass, no NVLink drain at the producer's end.
 // Measured alternatives (2 GPUs, 1 M dof per GPU, us per iteration): the producer CTA waiting for the
 // peers and storing the global sum for a poll-free consumer 57.7; the producer looking once and the
-// consumer polling only when that failed 58.7; post + collect (this, round 1's scheme) 54.8.
+// consumer polling only when that failed 58.7; post + collect (round 1's scheme) 54.8, 48.4 after K1's
+// push warp; exchange() 46.6; every producer CTA sending its partial to every rank 54.7.
 // all_reduce() = post + collect by one CTA (init kernel: once per solve).
 // NoComm: single GPU, everything compiles away.
 struct NoComm {
