@@ -309,13 +309,14 @@ struct PeerComm {
 
 	// Called by every thread after the kernel's gate.  The boundary entries leave at the START of the
 	// kernel that consumes the vector, while the other warps already stream the matrix; the neighbours
-	// only need them for their last slices.  A push costs its warp ~5 us (gather, NVLink stores, a
-	// system-scope fence, the ticket), so WHICH warps push decides the kernel's tail: the CTAs of a
-	// programmatically launched grid become resident in blockIdx order as the predecessor's CTAs retire,
-	// so the FIRST CTAs start (and finish) microseconds before the last ones (timeline, 1 M dof: CTA 0 is
-	// done 4 us before the last CTA).  The push is therefore given to one warp of each of the first CTAs,
-	// 32 values each -- it sits in their slack and leaves as early as possible; on the last CTAs (round 1)
-	// it extended the kernel by 5 us per iteration.
+	// only need them for their late slices.  A push costs its warp 5-6 us (index load, value load, NVLink
+	// stores, a system-scope fence until NVLink acknowledges, the ticket), and slices are dealt statically,
+	// so WHICH warps push decides the kernel's tail.  The pushing warp is the LAST warp of each of the first
+	// ceil(sends / 32) CTAs: the extra push-only warp where the kernel is launched with one
+	// (krylov_kernels.cuh, PUSH_WARP: 2 GPUs 53.5 -> 48.7 us per iteration), else the last streaming warp.
+	// First CTAs rather than last: the CTAs of a programmatically launched grid become resident in blockIdx
+	// order as the predecessor's CTAs retire, so the first ones start earliest (53.5 -> 52.3 before the push
+	// warp existed).
 	__device__ __forceinline__ void push_halo(const double *v_own, int which, unsigned long long seq,
 						  unsigned int *ticket) const
 	{
