@@ -185,3 +185,43 @@ def test_streamed_kernels_fit_two_ctas_per_sm():
     if "UBLKCP" not in sass:    # older cuobjdump builds want the mangled name
         sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass
+
+
+def test_committed_bench_lines_keep_the_contract():
+    """The bench lines under profiles/ (what DESIGN.md and the summaries quote) carry every key of the bench contract,
+    one peak number, green parity blocks and iteration counts that do not depend on the GPU count's arithmetic."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    baseline = json.load(open(os.path.join(root, "BASELINE.json")))
+    iters = {1: 4543, 2: 5965, 4: 7806, 8: 10319}
+    for n in (1, 2, 4, 8):
+        for suffix in ("", "_fused") if n > 1 else ("",):
+            line = json.loads(open(os.path.join(root, "profiles", "r02_bench_n%d%s.json" % (n, suffix))).read())
+            for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                        "scaling", "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+                assert key in line, (n, suffix, key)
+            assert line["n_gpus"] == n and line["dtype"] == "f64" and line["scaling"] == "weak"
+            assert line["metric"] == "pcg_dof_iter_per_s" and line["unit"] == "DOF*iter/s" and "DOF" in baseline["metric"]
+            assert line["vs_baseline"] is None and not baseline["published"]      # no published number to divide by
+            assert line["warmup"] >= 3 and line["gpu_launches"] > 0
+            assert line["roofline"]["peak"] == 6554.9 and line["roofline"]["bound"] == "hbm"
+            assert line["config"]["iterations_per_step"] == iters[n]
+            assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+            e2e = line["e2e"]
+            assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < line["value"]
+            if n == 1:
+                assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["value"] > 0
+                assert line["roofline"]["traffic"] and line["roofline"]["traffic_source"]["commit"]
+                assert line["target"]["l64_spmv"]["A_times_ones_matches_closed_form"]
+            else:
+                p = line["parity"]
+                assert p["ok"] and p["rows_bit_identical_to_single_gpu"] and p["K_bit_identical_to_cpu_reference"]
+                assert p["iterations"] == p["iterations_single_gpu"] == iters[n]
+            if suffix == "":
+                q = line["target"]["q16"]
+                layout = q["layout"] if n == 1 else q["local_block_layout"]
+                assert q["N_dof"] == 16012002 and q["iterations"] == 1000 and layout["idx16"] and layout["blocked"]
+                if n > 1:
+                    assert 0.5 < q["strong_scaling_efficiency"] <= 1.05
+    ref_line = json.loads(open(os.path.join(root, "profiles", "r02_bench_reference_n1.json")).read())
+    assert ref_line["impl"] == "reference" and ref_line["cpu_baseline"]["kind"] == "reference"
